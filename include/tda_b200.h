@@ -1,0 +1,80 @@
+/* tda_b200.h — C-ABI of the B200-native windowed-TDA engine (libtda_b200.so).
+ *
+ * The reference (Ignaciagothe/tda-eeg-audio) has no FFI of its own: its hot path is a chain of
+ * Python calls into scipy / numpy / ripser / persim.  Each entry point below replaces one of
+ * those call sites (cited per function) and is what a ctypes binding on the reference side
+ * would load.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes.  Unless the name ends in _host, every pointer is a
+ *     DEVICE pointer owned by the caller; the library allocates nothing persistent.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, and
+ *     performs no hidden synchronisation.  *_host variants take host pointers, stage through
+ *     their own pinned/device buffers and return after the results are in host memory.
+ *   - return value: 0 = ok, <0 = argument error (TDA_E_*), >0 = cudaError_t from the runtime.
+ *   - data-dependent conditions are reported per item in a `status` array, never by aborting
+ *     the batch (the reference's convention: a failing unit yields NaN / is skipped,
+ *     /root/reference/scripts/utils.py:188-191,
+ *     /root/reference/scripts/tda_eeg_classification_v2.py:565-567).
+ */
+#ifndef TDA_B200_H
+#define TDA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDA_E_ARG (-1)      /* bad argument (null pointer, negative size, ...)          */
+#define TDA_E_SIZE (-2)     /* size outside what the kernel family supports              */
+#define TDA_E_WORKSPACE (-3) /* workspace too small (see the matching *_workspace_bytes)  */
+
+/* per-item status bits */
+#define TDA_ST_OK 0
+#define TDA_ST_H1_TRUNCATED 1 /* more H1 bars than cap1; counts[.,1] holds the true count   */
+#define TDA_ST_NAN_INPUT 2    /* NaN in the upper triangle; those edges were left out       */
+#define TDA_ST_INTERNAL 4     /* internal capacity exhausted on the last tier (never for N<=64) */
+
+int tda_version(void);
+/* number of kernels this library has launched since load (all entry points; thread-safe) */
+unsigned long long tda_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Vietoris–Rips persistent homology, H0 and H1, Z/2, on a batch of small distance matrices.
+ * Replaces: ripser.ripser(dm, maxdim=1, thresh=t, distance_matrix=True)["dgms"]
+ *   /root/reference/scripts/utils.py:140 (compute_eeg_persistence)
+ *   /root/reference/scripts/utils.py:131 (compute_audio_persistence, after the distance stage)
+ *   /root/reference/scripts/tda_eeg_classification_v2.py:170-175 (compute_persistence_diagram)
+ *
+ * D       (B, N, ld) float32, item stride `strideB` elements (0 => N*ld); only D[b][i][j], i<j
+ *         is read (ripser reads the upper triangle of its float32 copy).  2 <= N <= 64.
+ * thresh  edges longer than thresh are absent; +inf => no threshold (ripser would substitute the
+ *         enclosing radius, which yields the same diagrams).
+ * bd0     (B, N, 2) float32  (birth, death) of H0, finite bars in ascending death order
+ *         (zero-length bars omitted), then one (0, +inf) per surviving component.
+ * pr0     (B, N, 2) int64    (birth vertex, death edge index C(i,2)+j), -1 = none.
+ * bd1     (B, cap1, 2) float32 (birth, death) of H1 in ripser's emission order (descending
+ *         birth edge in the filtration order); zero-persistence pairs omitted; (b, +inf) for
+ *         cycles still alive at thresh.
+ * pr1     (B, cap1, 2) int64  (birth edge index, death triangle index C(a,3)+C(b,2)+c), -1.
+ * counts  (B, 2) int32  number of rows written for H0 / H1 (true H1 count even if > cap1).
+ * status  (B) int32  TDA_ST_* bits.
+ * ws      workspace of at least tda_rips_h01_workspace_bytes(B, N) bytes (device).
+ * Any of pr0 / pr1 may be NULL (indices not wanted).
+ */
+size_t tda_rips_h01_workspace_bytes(int B, int N);
+int tda_rips_h01_batched(const float* D, int B, int N, int ld, long long strideB, float thresh,
+                         float* bd0, long long* pr0, float* bd1, long long* pr1, int* counts,
+                         int cap1, int* status, void* ws, size_t ws_bytes, void* stream);
+
+/* Same contract with HOST pointers: chunks the batch, overlaps H2D / kernels / D2H on internal
+ * streams, returns when all outputs are in host memory.  `device` is the CUDA ordinal. */
+int tda_rips_h01_host(const float* D, int B, int N, float thresh, float* bd0, long long* pr0,
+                      float* bd1, long long* pr1, int* counts, int cap1, int* status, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDA_B200_H */

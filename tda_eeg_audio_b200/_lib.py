@@ -1,0 +1,65 @@
+"""ctypes binding of libtda_b200.so (the C-ABI in include/tda_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing the import fails loudly, and every
+compute entry point refuses to run without a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtda_b200.so")
+
+_c = ctypes
+_vp, _i, _ll, _f, _sz = _c.c_void_p, _c.c_int, _c.c_longlong, _c.c_float, _c.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/tda_b200.h declares
+SIGNATURES = {
+    "tda_version": (_i, []),
+    "tda_launch_count": (_c.c_ulonglong, []),
+    "tda_rips_h01_workspace_bytes": (_sz, [_i, _i]),
+    "tda_rips_h01_batched": (_i, [_vp, _i, _i, _i, _ll, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    "tda_rips_h01_host": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i]),
+}
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m tda_eeg_audio_b200.build` "
+                "(nvcc, sm_100a). There is no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError => header/library mismatch, fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+class TdaError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str):
+    if rc == 0:
+        return
+    if rc < 0:
+        names = {-1: "TDA_E_ARG", -2: "TDA_E_SIZE", -3: "TDA_E_WORKSPACE"}
+        raise TdaError(f"{what}: {names.get(rc, rc)}")
+    raise TdaError(f"{what}: CUDA error {rc}")
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise TdaError("tda_eeg_audio_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def launch_count() -> int:
+    return int(load().tda_launch_count())

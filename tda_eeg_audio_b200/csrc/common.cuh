@@ -1,0 +1,9 @@
+// common.cuh — shared helpers of libtda_b200.so (host side bookkeeping only).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace tda {
+// every kernel launch made by the library goes through here so that
+// tda_launch_count() (bench.py's "gpu_launches") is a count, not a guess
+void count_launch(int n = 1);
+}  // namespace tda

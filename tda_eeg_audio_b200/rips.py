@@ -1,0 +1,91 @@
+"""Rips H0+H1 entry points.
+
+`ripser(...)` mirrors the third-party call the reference makes
+(/root/reference/scripts/utils.py:131,140; tda_eeg_classification_v2.py:170-175):
+`ripser(X, maxdim=1, thresh=..., distance_matrix=...)["dgms"]`.  `rips_h01_batched` is the
+batched tensor form (the fast path): one call for hundreds of thousands of windows.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def rips_h01_batched(D, thresh=float("inf"), cap1=None, want_pairs=True, out=None):
+    """D: CUDA float32 tensor (B, N, N) (any row stride; upper triangle is read), 2 <= N <= 64.
+
+    Returns dict of CUDA tensors: bd0 (B,N,2) f32, pr0 (B,N,2) i64, bd1 (B,cap1,2) f32,
+    pr1 (B,cap1,2) i64, counts (B,2) i32, status (B,) i32 — layout of include/tda_b200.h.
+    """
+    import torch
+    _lib.require_cuda()
+    lib = _lib.load()
+    if not (isinstance(D, torch.Tensor) and D.is_cuda and D.dtype == torch.float32 and D.dim() == 3):
+        raise TypeError("D must be a CUDA float32 tensor of shape (B, N, N)")
+    B, N, N2 = D.shape
+    if N != N2:
+        raise Exception("Distance matrix is not square")
+    if D.stride(2) != 1 or D.stride(1) < N:
+        D = D.contiguous()
+    if cap1 is None:
+        cap1 = max(N * (N - 1) // 2 - (N - 1), 1)
+    dev = D.device
+    if out is None:
+        out = {}
+    def buf(name, shape, dtype):
+        t = out.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            out[name] = t
+        return t
+    bd0 = buf("bd0", (B, N, 2), torch.float32)
+    bd1 = buf("bd1", (B, cap1, 2), torch.float32)
+    pr0 = buf("pr0", (B, N, 2), torch.int64) if want_pairs else None
+    pr1 = buf("pr1", (B, cap1, 2), torch.int64) if want_pairs else None
+    counts = buf("counts", (B, 2), torch.int32)
+    status = buf("status", (B,), torch.int32)
+    wsb = int(lib.tda_rips_h01_workspace_bytes(B, N))
+    if wsb == 0 and B > 0:
+        raise _lib.TdaError(f"rips_h01_batched: unsupported size N={N} (2 <= N <= 64)")
+    ws = buf("ws", (max(wsb, 16),), torch.uint8)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = lib.tda_rips_h01_batched(
+            D.data_ptr(), B, N, D.stride(1), D.stride(0) if B > 0 else 0, float(thresh), bd0.data_ptr(),
+            _ptr(pr0), bd1.data_ptr(), _ptr(pr1), counts.data_ptr(), cap1, status.data_ptr(),
+            ws.data_ptr(), wsb, stream)
+    _lib.check(rc, "tda_rips_h01_batched")
+    return out
+
+
+def ripser(X, maxdim=1, thresh=np.inf, coeff=2, distance_matrix=False, do_cocycles=False,
+           metric="euclidean", n_perm=None):
+    """Single-matrix drop-in for ripser.ripser (maxdim<=1, coeff=2 — all the reference uses).
+
+    numpy in, numpy out: {"dgms": [H0 (k,2) float64, H1 (k,2) float64], "pairs": [...]}."""
+    import torch
+    _lib.require_cuda()
+    if coeff != 2 or maxdim > 1 or do_cocycles or n_perm is not None or metric != "euclidean":
+        raise NotImplementedError("tda_eeg_audio_b200.ripser supports maxdim<=1, coeff=2, euclidean")
+    X = np.asarray(X)
+    if distance_matrix:
+        if X.ndim != 2 or X.shape[0] != X.shape[1]:
+            raise Exception("Distance matrix is not square")
+        dm = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).cuda()
+    else:
+        from .takens import pairwise_distance_f32  # device Gram-trick distance, f64 -> f32
+        dm = pairwise_distance_f32(torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).cuda()[None])[0]
+    r = rips_h01_batched(dm[None], thresh=float(thresh))
+    n0, n1 = (int(x) for x in r["counts"][0].tolist())
+    dg0 = r["bd0"][0, :n0].double().cpu().numpy().reshape(-1, 2)
+    dg1 = r["bd1"][0, :n1].double().cpu().numpy().reshape(-1, 2)
+    pr0 = r["pr0"][0, :n0].cpu().numpy()
+    pr1 = r["pr1"][0, :n1].cpu().numpy()
+    dgms = [dg0] + ([dg1] if maxdim >= 1 else [])
+    return {"dgms": dgms, "pairs": [pr0] + ([pr1] if maxdim >= 1 else []), "cocycles": [[], []],
+            "num_edges": None, "dperm2all": None, "idx_perm": np.arange(dm.shape[0]), "r_cover": 0.0}

@@ -1,0 +1,144 @@
+"""GPU parity: the CUDA Rips engine (through the C-ABI) against the CPU oracle on identical
+float32 distance matrices.  Integer simplex pairs and float32 births/deaths must be BIT-EXACT."""
+import numpy as np
+import pytest
+
+from tests import inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_gpu(D, thresh, cap1=None):
+    import torch
+    from tda_eeg_audio_b200 import rips_h01_batched
+    r = rips_h01_batched(torch.from_numpy(D).cuda(), thresh=thresh, cap1=cap1)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in r.items() if k != "ws"}
+
+
+def _compare(D, thresh, cap1=None):
+    from oracle import rips
+    g = _run_gpu(D, thresh, cap1)
+    c = rips.rips_h01_batched(D, thresh, cap1=cap1)
+    assert np.array_equal(g["counts"], c["counts"]), np.nonzero((g["counts"] != c["counts"]).any(1))[0][:10]
+    B = len(D)
+    cap = c["bd1"].shape[1]
+    for b in range(B):
+        n0, n1 = c["counts"][b]
+        n1 = min(n1, cap)
+        assert np.array_equal(g["bd0"][b, :n0].view(np.uint32), c["bd0"][b, :n0].view(np.uint32)), b
+        assert np.array_equal(g["pr0"][b, :n0], c["pr0"][b, :n0]), b
+        assert np.array_equal(g["bd1"][b, :n1].view(np.uint32), c["bd1"][b, :n1].view(np.uint32)), b
+        assert np.array_equal(g["pr1"][b, :n1], c["pr1"][b, :n1]), b
+    return g, c
+
+
+def test_eeg_like_47(cuda):
+    D = inputs.eeg_like(np.random.default_rng(0), 512)
+    g, _ = _compare(D, 2.0)
+    assert (g["status"] == 0).all()
+
+
+def test_uniform_stress_47(cuda):
+    # ~100 H1 bars, up to ~80 simultaneous classes: exercises the W=4 and W=64 tiers
+    D = inputs.sym_uniform(np.random.default_rng(1), 256, 47)
+    _compare(D, 2.0)
+
+
+@pytest.mark.parametrize("q", [2, 8, 64])
+def test_ties_47(cuda, q):
+    D = inputs.sym_uniform(np.random.default_rng(2), 64, 47)
+    D = (np.round(D * q) / q).astype(np.float32)
+    _compare(D, 2.0)
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 16, 31, 32, 33, 47, 63, 64])
+def test_sizes(cuda, n):
+    rng = np.random.default_rng(10 + n)
+    D = inputs.sym_uniform(rng, 48, n)
+    _compare(D, np.inf)
+    _compare(D, 0.5)
+    Dq = (np.round(D * 8) / 8).astype(np.float32)
+    _compare(Dq, np.inf)
+
+
+def test_threshold_binding_and_essential_h1(cuda):
+    D = inputs.circle_cloud(np.random.default_rng(5), 64, 40)
+    g, c = _compare(D, 0.9)          # the big loop is still alive at 0.9 -> (b, inf) rows
+    assert np.isinf(c["bd1"]).any()
+    _compare(D, 3.0)
+
+
+def test_degenerate(cuda):
+    n = 47
+    ones = np.ones((1, n, n), np.float32)
+    zeros = np.zeros((1, n, n), np.float32)
+    sq2 = np.full((1, n, n), np.sqrt(2), np.float32)
+    D = np.concatenate([ones, zeros, sq2])
+    for b in range(len(D)):
+        np.fill_diagonal(D[b], 0)
+    _compare(D, 2.0)
+    _compare(D, 0.5)
+
+
+def test_only_upper_triangle_is_read(cuda):
+    D = inputs.eeg_like(np.random.default_rng(6), 16)
+    g1 = _run_gpu(D, 2.0)
+    D2 = D.copy()
+    il = np.tril_indices(47, -1)
+    D2[:, il[0], il[1]] = 123.0
+    D2[:, np.arange(47), np.arange(47)] = -5.0
+    g2 = _run_gpu(D2, 2.0)
+    for k in ("bd0", "pr0", "counts"):
+        assert np.array_equal(g1[k], g2[k])
+    n1 = g1["counts"][:, 1]
+    for b in range(16):
+        assert np.array_equal(g1["bd1"][b, :n1[b]], g2["bd1"][b, :n1[b]])
+
+
+def test_nan_edges_are_dropped(cuda):
+    D = inputs.eeg_like(np.random.default_rng(8), 8)
+    D[:, 3, 10] = np.nan
+    D[:, 10, 3] = np.nan
+    g, c = _compare(D, 2.0)
+    assert (g["status"] & 2).all()
+
+
+def test_cap1_truncation(cuda):
+    D = inputs.sym_uniform(np.random.default_rng(9), 8, 47)
+    g, c = _compare(D, 2.0, cap1=16)
+    assert (g["status"] & 1).all() and (g["counts"][:, 1] > 16).all()
+
+
+def test_host_entry_point(cuda):
+    import ctypes
+    from tda_eeg_audio_b200 import _lib
+    from oracle import rips
+    D = inputs.eeg_like(np.random.default_rng(11), 300)
+    B, n, cap1 = len(D), 47, 64
+    bd0 = np.zeros((B, n, 2), np.float32); pr0 = np.zeros((B, n, 2), np.int64)
+    bd1 = np.zeros((B, cap1, 2), np.float32); pr1 = np.zeros((B, cap1, 2), np.int64)
+    counts = np.zeros((B, 2), np.int32); status = np.zeros(B, np.int32)
+    rc = _lib.load().tda_rips_h01_host(D.ctypes.data, B, n, 2.0, bd0.ctypes.data, pr0.ctypes.data,
+                                       bd1.ctypes.data, pr1.ctypes.data, counts.ctypes.data, cap1,
+                                       status.ctypes.data, 0)
+    assert rc == 0
+    c = rips.rips_h01_batched(D, 2.0, cap1=cap1)
+    assert np.array_equal(counts, c["counts"])
+    for b in range(B):
+        n1 = counts[b, 1]
+        assert np.array_equal(bd1[b, :n1], c["bd1"][b, :n1]) and np.array_equal(pr1[b, :n1], c["pr1"][b, :n1])
+        assert np.array_equal(bd0[b], c["bd0"][b]) and np.array_equal(pr0[b], c["pr0"][b])
+
+
+def test_ripser_shim(cuda):
+    from tda_eeg_audio_b200 import ripser
+    from oracle import rips
+    D = inputs.eeg_like(np.random.default_rng(12), 1)[0].astype(np.float64)
+    a = ripser(D, maxdim=1, thresh=2.0, distance_matrix=True)
+    b = rips.ripser(D, maxdim=1, thresh=2.0, distance_matrix=True)
+    for k in range(2):
+        assert a["dgms"][k].dtype == np.float64 and np.array_equal(a["dgms"][k], b["dgms"][k])
+        assert np.array_equal(a["pairs"][k], b["pairs"][k])
+    with pytest.raises(Exception, match="not square"):
+        ripser(np.zeros((3, 4)), distance_matrix=True)
