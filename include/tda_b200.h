@@ -40,6 +40,13 @@ extern "C" {
 int tda_version(void);
 /* number of kernels this library has launched since load (all entry points; thread-safe) */
 unsigned long long tda_launch_count(void);
+/* Per-kernel timing with CUDA events recorded on the launching stream around every launch the
+ * library makes while enabled (enable(1) clears earlier samples, enable(0) stops and clears).
+ * query() synchronises the recorded events of kernel `kernel` ("rips_small_w2", "rips_small_w4",
+ * "rips_small_w64", "pers_features", "aggregate_windows", ...) and returns their summed
+ * duration and count. */
+int tda_profile_enable(int on);
+int tda_profile_query(const char* kernel, double* total_ms, int* launches);
 
 /* ------------------------------------------------------------------------------------------
  * Vietoris–Rips persistent homology, H0 and H1, Z/2, on a batch of small distance matrices.
@@ -73,6 +80,36 @@ int tda_rips_h01_batched(const float* D, int B, int N, int ld, long long strideB
  * streams, returns when all outputs are in host memory.  `device` is the CUDA ordinal. */
 int tda_rips_h01_host(const float* D, int B, int N, float thresh, float* bd0, long long* pr0,
                       float* bd1, long long* pr1, int* counts, int cap1, int* status, int device);
+
+/* ------------------------------------------------------------------------------------------
+ * Persistence statistics / entropy features of a batch of diagrams.
+ * Replaces: extract_features  /root/reference/scripts/utils.py:144-177
+ *         ≡ extract_persistence_features  /root/reference/scripts/tda_eeg_classification_v2.py:179-250
+ * bd     (B, cap, 2) float32 rows (birth, death), padded; row count of item b is
+ *        counts[b*count_stride] (clamped to cap) — pass counts+0 / counts+1 with stride 2 for the
+ *        H0 / H1 outputs of tda_rips_h01_batched.
+ * feats  item b gets 11 float64 at feats[b*feat_stride ...]: n_features, n_essential, mean_birth,
+ *        std_birth, mean_death, std_death, mean_persistence, std_persistence, max_persistence,
+ *        total_persistence, persistence_entropy (np.std ddof=0; std := 0 when <= 1 finite row;
+ *        all zero except n_essential when no finite row).
+ */
+int tda_pers_features(const float* bd, int cap, const int* counts, int count_stride, int B,
+                      double* feats, int feat_stride, void* stream);
+
+/* Mean / std (ddof=0) over the windows of every (recording, band, H0|H1, feature).
+ * Replaces: /root/reference/scripts/tda_eeg_classification_v2.py:429-436.
+ * feats (R, Bd, Wn, 2, 11) float64 -> table (R, Bd*44) float64, column order of
+ * /root/reference/features/feature_names.txt: band*44 + feat*4 + {h0_mean,h0_std,h1_mean,h1_std}. */
+int tda_aggregate_windows(const double* feats, int R, int Bd, int Wn, double* table, void* stream);
+
+/* End-to-end host entry for the EEG feature path: host distance matrices in, host feature table
+ * out (process_file_features, /root/reference/scripts/tda_eeg_classification_v2.py:338-442, for
+ * R recordings x Bd bands x Wn windows at once).  D (R,Bd,Wn,N,N) float32 HOST.  Optional host
+ * outputs (NULL to skip): bd0 (B,N,2), bd1 (B,cap1,2), counts (B,2), status (B), feats (B,2,11);
+ * table (R, Bd*44) float64 is mandatory.  Chunked over three streams; returns when done. */
+int tda_eeg_features_host(const float* D, int R, int Bd, int Wn, int N, float thresh, int cap1,
+                          float* bd0, float* bd1, int* counts, int* status, double* feats,
+                          double* table, int device);
 
 #ifdef __cplusplus
 }

@@ -18,8 +18,13 @@ _vp, _i, _ll, _f, _sz = _c.c_void_p, _c.c_int, _c.c_longlong, _c.c_float, _c.c_s
 SIGNATURES = {
     "tda_version": (_i, []),
     "tda_launch_count": (_c.c_ulonglong, []),
+    "tda_profile_enable": (_i, [_i]),
+    "tda_profile_query": (_i, [_c.c_char_p, _c.POINTER(_c.c_double), _c.POINTER(_c.c_int)]),
     "tda_rips_h01_workspace_bytes": (_sz, [_i, _i]),
     "tda_rips_h01_batched": (_i, [_vp, _i, _i, _i, _ll, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    "tda_pers_features": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp]),
+    "tda_aggregate_windows": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "tda_eeg_features_host": (_i, [_vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "tda_rips_h01_host": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i]),
 }
 
@@ -63,3 +68,14 @@ def require_cuda():
 
 def launch_count() -> int:
     return int(load().tda_launch_count())
+
+
+def profile_enable(on: bool):
+    load().tda_profile_enable(1 if on else 0)
+
+
+def profile_query(kernel: str):
+    """(total_ms, launches) of `kernel` since profile_enable(True); synchronises its events."""
+    ms, n = _c.c_double(0), _c.c_int(0)
+    check(load().tda_profile_query(kernel.encode(), _c.byref(ms), _c.byref(n)), "tda_profile_query")
+    return ms.value, n.value

@@ -656,6 +656,7 @@ static WsLayout ws_layout(int B, int N) {
 
 template <int W, bool G>
 static cudaError_t launch_tier(const Params& p, int warps_per_block, int grid, cudaStream_t st) {
+    ProfScope prof(W == 2 ? "rips_small_w2" : (W == 4 ? "rips_small_w4" : "rips_small_w64"), st);
     size_t smem = Layout<W, G>::bytes(p.N) * warps_per_block;
     cudaError_t e = cudaFuncSetAttribute(rips_small_kernel<W, G>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -1,0 +1,42 @@
+"""Generates tests/golden/*.npz by running the REFERENCE's own functions in the build container
+(/root/reference/scripts/utils.py imported where it lies, with ripser/persim replaced by the CPU
+oracle — oracle/reference_import.py).  The fixtures travel to the GPU box; the reference does not.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import reference_import  # noqa: E402
+from tests import inputs  # noqa: E402
+
+
+def main():
+    u = reference_import.load_utils()
+    rng = np.random.default_rng(20261018)
+    # ---- features: reference extract_features on diagrams of the reference's own persistence calls
+    out = {}
+    dgms = []
+    for D in inputs.eeg_like(rng, 4):
+        dgms += u.compute_eeg_persistence(D.astype(np.float64))
+    for D in inputs.sym_uniform(rng, 2, 47):
+        dgms += u.compute_eeg_persistence(D.astype(np.float64))
+    dgms += [np.zeros((0, 2)), np.array([[0.0, np.inf]]), np.array([[0.1, 0.4]]),
+             np.array([[0.0, 0.0], [0.0, 0.0]])]
+    for k, d in enumerate(dgms):
+        f = u.extract_features(d)
+        out[f"dgm{k}"] = np.asarray(d, np.float64)
+        out[f"feat{k}"] = np.array([float(v) for v in f.values()])
+    out["n"] = len(dgms)
+    out["names"] = np.array(list(u.extract_features(dgms[0]).keys()))
+    np.savez_compressed(os.path.join(HERE, "features.npz"), **out)
+    print("features.npz:", len(dgms), "diagrams")
+
+
+if __name__ == "__main__":
+    main()

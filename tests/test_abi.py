@@ -1,0 +1,52 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/tda_b200.h declares."""
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "tda_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(tda_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported_and_bound():
+    from tda_eeg_audio_b200 import _lib
+    lib = _lib.load()
+    names = _declared()
+    assert len(names) >= 8
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in tda_b200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in _lib.py"
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_argument_errors_without_gpu():
+    from tda_eeg_audio_b200 import _lib
+    lib = _lib.load()
+    assert lib.tda_version() >= 100
+    assert lib.tda_rips_h01_workspace_bytes(10, 65) == 0
+    assert lib.tda_rips_h01_workspace_bytes(10, 47) > 0
+    # null pointers / bad sizes are rejected before any CUDA call
+    assert lib.tda_rips_h01_batched(None, 1, 47, 47, 0, 2.0, None, None, None, None, None, 1, None, None, 0, None) == -1
+    assert lib.tda_pers_features(None, 1, None, 1, 1, None, 11, None) == -1
+
+
+def test_no_cpu_fallback():
+    import pytest
+    import torch
+    from tda_eeg_audio_b200 import _lib, rips_h01_batched
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.TdaError):
+        rips_h01_batched(torch.zeros((1, 4, 4)))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "tda_eeg_audio_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("oracle/pcoh_model.py", ""), f"{f} mentions the oracle"
