@@ -76,6 +76,16 @@ int tda_rips_h01_batched(const float* D, int B, int N, int ld, long long strideB
                          float* bd0, long long* pr0, float* bd1, long long* pr1, int* counts,
                          int cap1, int* status, void* ws, size_t ws_bytes, void* stream);
 
+/* Rips H0+H1 for medium matrices, 2 <= N <= 254 (the Takens clouds of the audio path), one CTA per
+ * cloud.  Same outputs and conventions as tda_rips_h01_batched; differences: `npts` (may be NULL)
+ * gives the point count of every item (<= N, the leading npts x npts block of the ld x ld matrix
+ * is used), and the H0 output has an explicit row capacity cap0 (bd0 (B, cap0, 2)).
+ * Replaces ripser(...) inside compute_audio_persistence, /root/reference/scripts/utils.py:131. */
+size_t tda_rips_h01_medium_workspace_bytes(int B, int N);
+int tda_rips_h01_medium(const float* D, const int* npts, int B, int N, int ld, long long strideB,
+                        float thresh, float* bd0, long long* pr0, int cap0, float* bd1, long long* pr1,
+                        int cap1, int* counts, int* status, void* ws, size_t ws_bytes, void* stream);
+
 /* Same contract with HOST pointers: chunks the batch, overlaps H2D / kernels / D2H on internal
  * streams, returns when all outputs are in host memory.  `device` is the CUDA ordinal. */
 int tda_rips_h01_host(const float* D, int B, int N, float thresh, float* bd0, long long* pr0,
@@ -101,6 +111,67 @@ int tda_pers_features(const float* bd, int cap, const int* counts, int count_str
  * feats (R, Bd, Wn, 2, 11) float64 -> table (R, Bd*44) float64, column order of
  * /root/reference/features/feature_names.txt: band*44 + feat*4 + {h0_mean,h0_std,h1_mean,h1_std}. */
 int tda_aggregate_windows(const double* feats, int R, int Bd, int Wn, double* table, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Zero-phase IIR filtering of many sequences at once, FP64, scipy's exact recursion
+ * (odd extension by padlen, zi scaled by the first sample, forward pass, reverse, second pass).
+ * Replaces: signal.sosfiltfilt(sos, x)  /root/reference/notebooks/1_preprocesamiento.ipynb:262-263  (form 0)
+ *           sig_proc.filtfilt(b, a, x)  /root/reference/scripts/utils.py:63,74                    (form 1)
+ * x      n_seq rows of T float64 samples, row stride x_stride (0 => T).
+ * form   0: coef = n_bands x n x 6 (sos rows b0 b1 b2 a0 a1 a2), zi = n_bands x n x 2 (sosfilt_zi), n <= 4
+ *        1: coef = n_bands x 2 x n (b then a), zi = n_bands x (n-1) (lfilter_zi), n <= 9 taps
+ *        (coefficients / zi are HOST pointers: a few dozen doubles designed once per band.)
+ * padlen 3*ntaps as scipy computes it (27 for the order-4 band-pass, 15 for the order-4 low-pass).
+ * y      (n_bands, n_seq, T) float64: every band's filter applied to every sequence.
+ * ws     tda_filtfilt_workspace_bytes(...) bytes (the padded forward-pass intermediate).
+ */
+size_t tda_filtfilt_workspace_bytes(long long n_seq, int n_bands, long long T, int padlen);
+int tda_filtfilt_f64(const double* x, long long n_seq, long long T, long long x_stride, int form,
+                     int n_bands, int n, const double* coef, const double* zi, int padlen, double* y,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Sliding windows -> Pearson correlation -> correlation distance, fused (windows never stored).
+ * Replaces: create_sliding_windows      /root/reference/notebooks/1_preprocesamiento.ipynb:314-364
+ *           compute_correlation_matrix  /root/reference/notebooks/2_graph_construction.ipynb:86-97
+ *           correlation_to_distance     /root/reference/notebooks/2_graph_construction.ipynb:100-122
+ * x       (R, C, T) float64, recording stride strideR (0 => C*T); windows start at w*step,
+ *         W = (T-win)/step + 1 of them (none if T < win).
+ * method  0 "euclidean" sqrt(2(1-r)) [the pipeline's], 1 "abs" 1-|r|, 2 "standard" 1-r, 3 "sqrt" sqrt(1-r^2).
+ * D       float32 distances, corr float64 correlations (either may be NULL); window (rec, w) is
+ *         written at rec*strideO + w*C*C (strideO 0 => W*C*C), both triangles, zero diagonal in D.
+ */
+int tda_corrdist_windows(const double* x, int R, int C, long long T, long long strideR, int win, int step,
+                         int method, float* D, double* corr, long long strideO, void* stream);
+
+/* correlation_to_distance on one n x n float64 correlation matrix (float64 out), methods as above.
+ * Replaces: /root/reference/notebooks/2_graph_construction.ipynb:100-122. */
+int tda_corr_to_dist_f64(const double* corr, int n, int method, double* dist, void* stream);
+
+/* (D + D^T)/2, zero diagonal, max(.,0), cast to float32 for B matrices: the float64 preamble of
+ * compute_eeg_persistence (/root/reference/scripts/utils.py:137-139) ≡ compute_persistence_diagram
+ * (/root/reference/scripts/tda_eeg_classification_v2.py:166-168) before ripser's float32 cast. */
+int tda_symmetrize_f64_to_f32(const double* D, long long B, int n, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Audio side: delay, Takens embedding, pairwise distances.
+ * tda_compute_tau     replaces compute_tau  /root/reference/scripts/utils.py:92-104
+ *   wins (B rows of L float64, row stride `stride`, 0 => L); max_lag < 0 => L/4 (the default);
+ *   tau[b] = first i in [1, min(max_lag, L-1)) with autocorrelation <= 0, else max(max_lag/10, 1).
+ * tda_takens_cloud    replaces takens_embedding (utils.py:107-116) + the min-max normalisation of
+ *   compute_audio_persistence (utils.py:127-130, skipped when normalise == 0)
+ *   tau[b*tau_stride] is the delay of item b (tau_stride 0 => one shared delay);
+ *   pts (B, ldp, dim) float64, npts[b] = ceil((L-(dim-1)tau)/subsample) clamped to [0, ldp].
+ * tda_pairwise_dist_f32  replaces sklearn pairwise_distances inside ripser(point_cloud)
+ *   (float64 Gram trick, max(.,0), zero diagonal, sqrt, cast to float32); npts may be NULL (= ldp);
+ *   D (B, ld, ld) float32, only the leading npts[b] x npts[b] block is written. */
+int tda_compute_tau(const double* wins, long long B, int L, long long stride, int max_lag, int* tau,
+                    void* stream);
+int tda_takens_cloud(const double* wins, long long B, int L, long long stride, const int* tau,
+                     int tau_stride, int dim, int subsample, int normalise, int ldp, double* pts,
+                     int* npts, void* stream);
+int tda_pairwise_dist_f32(const double* pts, const int* npts, long long B, int ldp, int dim, int ld,
+                          float* D, void* stream);
 
 /* End-to-end host entry for the EEG feature path: host distance matrices in, host feature table
  * out (process_file_features, /root/reference/scripts/tda_eeg_classification_v2.py:338-442, for

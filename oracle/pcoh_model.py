@@ -138,26 +138,72 @@ def rips_h01_pcoh(dm, thresh=np.inf, stats=None):
             adj[i] |= 1 << j
             adj[j] |= 1 << i
         else:
-            # ---------------- tie run: exact simplexwise order
-            tris = []
+            # ---------------- tie run: exact simplexwise order, with apparent pairs inside the run
+            # pass 1: all edges of the run enter (H0 decisions in rank order)
+            run = []
+            runadj = [0] * n
             for p in range(r, r1):
                 _, idx, i, j = edges[p]
-                G = adj[i] & adj[j]  # both other edges strictly earlier than this edge
                 merging = h0_step(d, idx, i, j)
-                if not merging:
-                    new_class(p, i, j)
                 adj[i] |= 1 << j
                 adj[j] |= 1 << i
+                runadj[i] |= 1 << j
+                runadj[j] |= 1 << i
+                run.append((p, idx, i, j, merging))
+
+            def earlier(x, y, idx_e):
+                # is edge (x,y) earlier in the filtration than the run edge with index idx_e ?
+                if not (runadj[x] >> y) & 1:
+                    return True
+                a, b = max(x, y), min(x, y)
+                return _c2(a) + b > idx_e
+
+            # pass 2: a cycle-creating run edge whose FIRST cofacet (largest apex among the
+            # triangles present after the run) has it as youngest edge forms an apparent pair:
+            # no slot; the cocycles are extended over it when that triangle is reached.
+            defv = {}
+            groups = {}
+            for (p, idx, i, j, merging) in run:
+                cand = adj[i] & adj[j]
+                g = 0
                 v = 0
-                while G:
-                    if G & 1:
+                c = cand
+                while c:
+                    if (c & 1) and earlier(i, v, idx) and earlier(j, v, idx):
+                        g |= 1 << v
+                    c >>= 1
+                    v += 1
+                groups[(i, j)] = g
+                if merging:
+                    continue
+                vt = cand.bit_length() - 1
+                if cand and earlier(i, vt, idx) and earlier(j, vt, idx):
+                    defv[(i, j)] = vt
+                else:
+                    new_class(p, i, j)
+            tris = []
+            for (p, idx, i, j, merging) in run:
+                g = groups[(i, j)]
+                v = 0
+                while g:
+                    if g & 1:
                         tris.append((tri_index(i, j, v), i, j, v))
-                    G >>= 1
+                    g >>= 1
                     v += 1
             tris.sort(reverse=True)
+
+            def val(rec, x, y):
+                return (rec["phi"][x] >> y) & 1
+
             for (t, i, j, v) in tris:
-                cands = [rec for rec in live
-                         if ((rec["phi"][i] >> j) ^ (rec["phi"][i] >> v) ^ (rec["phi"][j] >> v)) & 1]
+                if defv.get((i, j)) == v:
+                    # defining triangle of the apparent edge (i,j): phi(i,j) := phi(i,v)+phi(j,v)
+                    for rec in live:
+                        if val(rec, i, v) ^ val(rec, j, v):
+                            rec["phi"][i] |= 1 << j
+                            rec["phi"][j] |= 1 << i
+                    continue
+                cands = [rec for rec in live if val(rec, i, j) ^ val(rec, i, v) ^ val(rec, j, v)]
                 if cands:
                     kill_at(cands, t, d)
         max_live = max(max_live, len(live))

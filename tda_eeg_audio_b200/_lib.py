@@ -24,7 +24,17 @@ SIGNATURES = {
     "tda_rips_h01_batched": (_i, [_vp, _i, _i, _i, _ll, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "tda_pers_features": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp]),
     "tda_aggregate_windows": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "tda_filtfilt_workspace_bytes": (_sz, [_ll, _i, _ll, _i]),
+    "tda_filtfilt_f64": (_i, [_vp, _ll, _ll, _ll, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    "tda_corrdist_windows": (_i, [_vp, _i, _i, _ll, _ll, _i, _i, _i, _vp, _vp, _ll, _vp]),
+    "tda_corr_to_dist_f64": (_i, [_vp, _i, _i, _vp, _vp]),
+    "tda_symmetrize_f64_to_f32": (_i, [_vp, _ll, _i, _vp, _vp]),
+    "tda_compute_tau": (_i, [_vp, _ll, _i, _ll, _i, _vp, _vp]),
+    "tda_takens_cloud": (_i, [_vp, _ll, _i, _ll, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "tda_pairwise_dist_f32": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp]),
     "tda_eeg_features_host": (_i, [_vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "tda_rips_h01_medium_workspace_bytes": (_sz, [_i, _i]),
+    "tda_rips_h01_medium": (_i, [_vp, _vp, _i, _i, _i, _ll, _f, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "tda_rips_h01_host": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i]),
 }
 

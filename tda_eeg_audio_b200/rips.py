@@ -16,11 +16,14 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
-def rips_h01_batched(D, thresh=float("inf"), cap1=None, want_pairs=True, out=None):
-    """D: CUDA float32 tensor (B, N, N) (any row stride; upper triangle is read), 2 <= N <= 64.
+def rips_h01_batched(D, thresh=float("inf"), cap1=None, want_pairs=True, out=None, npts=None, engine="auto"):
+    """D: CUDA float32 tensor (B, N, N) (any row stride; upper triangle is read), 2 <= N <= 254.
 
-    Returns dict of CUDA tensors: bd0 (B,N,2) f32, pr0 (B,N,2) i64, bd1 (B,cap1,2) f32,
-    pr1 (B,cap1,2) i64, counts (B,2) i32, status (B,) i32 — layout of include/tda_b200.h.
+    N <= 64 runs the warp-per-window engine (rips_small), larger N the CTA-per-cloud engine
+    (rips_medium); `npts` (CUDA int32 (B,), medium engine only) gives per-item point counts for
+    padded batches.  Returns dict of CUDA tensors: bd0 (B,N,2) f32, pr0 (B,N,2) i64,
+    bd1 (B,cap1,2) f32, pr1 (B,cap1,2) i64, counts (B,2) i32, status (B,) i32 — layout of
+    include/tda_b200.h.
     """
     import torch
     _lib.require_cuda()
@@ -32,6 +35,8 @@ def rips_h01_batched(D, thresh=float("inf"), cap1=None, want_pairs=True, out=Non
         raise Exception("Distance matrix is not square")
     if D.stride(2) != 1 or D.stride(1) < N:
         D = D.contiguous()
+    if engine == "auto":
+        engine = "small" if (N <= 64 and npts is None) else "medium"
     if cap1 is None:
         cap1 = max(N * (N - 1) // 2 - (N - 1), 1)
     dev = D.device
@@ -49,17 +54,29 @@ def rips_h01_batched(D, thresh=float("inf"), cap1=None, want_pairs=True, out=Non
     pr1 = buf("pr1", (B, cap1, 2), torch.int64) if want_pairs else None
     counts = buf("counts", (B, 2), torch.int32)
     status = buf("status", (B,), torch.int32)
-    wsb = int(lib.tda_rips_h01_workspace_bytes(B, N))
+    if engine == "small":
+        wsb = int(lib.tda_rips_h01_workspace_bytes(B, N))
+    else:
+        wsb = int(lib.tda_rips_h01_medium_workspace_bytes(B, N))
     if wsb == 0 and B > 0:
-        raise _lib.TdaError(f"rips_h01_batched: unsupported size N={N} (2 <= N <= 64)")
+        raise _lib.TdaError(f"rips_h01_batched: unsupported size N={N} for engine {engine}")
     ws = buf("ws", (max(wsb, 16),), torch.uint8)
+    sB = D.stride(0) if B > 0 else 0
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream().cuda_stream
-        rc = lib.tda_rips_h01_batched(
-            D.data_ptr(), B, N, D.stride(1), D.stride(0) if B > 0 else 0, float(thresh), bd0.data_ptr(),
-            _ptr(pr0), bd1.data_ptr(), _ptr(pr1), counts.data_ptr(), cap1, status.data_ptr(),
-            ws.data_ptr(), wsb, stream)
-    _lib.check(rc, "tda_rips_h01_batched")
+        if engine == "small":
+            rc = lib.tda_rips_h01_batched(
+                D.data_ptr(), B, N, D.stride(1), sB, float(thresh), bd0.data_ptr(),
+                _ptr(pr0), bd1.data_ptr(), _ptr(pr1), counts.data_ptr(), cap1, status.data_ptr(),
+                ws.data_ptr(), wsb, stream)
+        else:
+            if npts is not None:
+                assert npts.is_cuda and npts.dtype == torch.int32 and npts.shape == (B,)
+                npts = npts.contiguous()
+            rc = lib.tda_rips_h01_medium(
+                D.data_ptr(), _ptr(npts), B, N, D.stride(1), sB, float(thresh), bd0.data_ptr(), _ptr(pr0), N,
+                bd1.data_ptr(), _ptr(pr1), cap1, counts.data_ptr(), status.data_ptr(), ws.data_ptr(), wsb, stream)
+    _lib.check(rc, "tda_rips_h01_" + engine)
     return out
 
 

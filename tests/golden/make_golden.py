@@ -40,3 +40,30 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def signal_golden():
+    """utils.bandpass_filter / create_windows / compute_tau / takens_embedding from the reference's
+    own module, on seeded inputs."""
+    u = reference_import.load_utils()
+    rng = np.random.default_rng(7)
+    out = {}
+    env = np.abs(rng.standard_normal(3000)) + 0.3 * np.sin(np.arange(3000) / 40.0)
+    out["env"] = env
+    for name, (lo, hi) in u.FREQ_BANDS.items():
+        out[f"bp_{name}"] = u.bandpass_filter(env, 250, lo, hi)
+    out["windows_alpha"] = u.create_windows(out["bp_alpha"], 250, 62)
+    taus = []
+    for name in u.FREQ_BANDS:
+        wins = u.create_windows(out[f"bp_{name}"], 250, 62)
+        taus.append([u.compute_tau(w, max_lag=125) for w in wins])
+    out["taus"] = np.array(taus)
+    w0 = out["windows_alpha"][0]
+    out["takens_tau7_sub2"] = u.takens_embedding(w0, 3, 7, 2)
+    out["takens_tau12_sub1"] = u.takens_embedding(w0, 3, 12, 1)
+    np.savez_compressed(os.path.join(HERE, "signal.npz"), **out)
+    print("signal.npz:", sorted(out))
+
+
+if __name__ == "__main__":
+    signal_golden()

@@ -1,0 +1,35 @@
+"""CPU-only: the signal oracle against the fixtures generated from the reference's own utils.py
+(tests/golden/signal.npz), and the host-side drop-ins that need no GPU."""
+import os
+
+import numpy as np
+
+from oracle import signal_ref
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "signal.npz"))
+
+
+def test_bandpass_ba_matches_reference_fixture():
+    for name, (lo, hi) in signal_ref.FREQ_BANDS.items():
+        got = signal_ref.bandpass_filter(G["env"], 250, lo, hi)
+        np.testing.assert_allclose(got, G[f"bp_{name}"], rtol=0, atol=1e-12 * np.abs(G[f"bp_{name}"]).max())
+
+
+def test_windows_tau_takens_match_reference_fixture():
+    assert np.array_equal(signal_ref.create_windows(G["bp_alpha"], 250, 62), G["windows_alpha"])
+    for b, name in enumerate(signal_ref.FREQ_BANDS):
+        wins = signal_ref.create_windows(G[f"bp_{name}"], 250, 62)
+        assert [signal_ref.compute_tau(w, max_lag=125) for w in wins] == list(G["taus"][b])
+    w0 = G["windows_alpha"][0]
+    assert np.array_equal(signal_ref.takens_embedding(w0, 3, 7, 2), G["takens_tau7_sub2"])
+    assert np.array_equal(signal_ref.takens_embedding(w0, 3, 12, 1), G["takens_tau12_sub1"])
+
+
+def test_window_dropins_are_pure_slicing():
+    from tda_eeg_audio_b200 import dsp
+    x = np.random.default_rng(4).standard_normal((3, 1000))
+    a, ta = dsp.create_sliding_windows(x, 1.0, 0.75, 250)
+    b, tb = signal_ref.create_sliding_windows(x, 1.0, 0.75, 250)
+    assert np.array_equal(a, b) and np.array_equal(ta, tb)
+    assert np.array_equal(dsp.create_windows(x[0], 250, 62), signal_ref.create_windows(x[0], 250, 62))
+    assert dsp.create_windows(x[0][:100], 250, 62).shape == (0, 250)
