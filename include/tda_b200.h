@@ -173,6 +173,23 @@ int tda_takens_cloud(const double* wins, long long B, int L, long long stride, c
 int tda_pairwise_dist_f32(const double* pts, const int* npts, long long B, int ldp, int dim, int ld,
                           float* D, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Exact 1-Wasserstein distance between persistence diagrams, batched (L2 ground metric,
+ * Euclidean distance to the diagonal, sum of matched costs), float64.
+ * Replaces: safe_wasserstein -> persim.wasserstein  /root/reference/scripts/utils.py:180-191
+ *           (per-window calls at /root/reference/scripts/tda_eeg_audio_comparison.py:95-96,
+ *            /root/reference/scripts/matched_vs_mismatched.py:87-95).
+ * bdA (., capA, 2) / bdB (., capB, 2) float32 padded diagrams; row counts nA[i*nA_stride],
+ * nB[i*nB_stride] (clamped to the caps).  Rows with a non-finite coordinate are ignored; an empty
+ * diagram counts as the single point (0,0), as safe_wasserstein does.  Pair k compares diagram
+ * idxA[k] of A with diagram idxB[k] of B (NULL => k), so matched and mismatched pairings need no
+ * copies.  out[k] float64.  limA / limB (0 => the cap) are upper bounds on the row counts actually
+ * present (rows beyond them are ignored); shared memory is sized by them:
+ * 8 * min(limA,limB) * max(limA,limB) bytes must fit in 227 KB and limA + limB <= 1022. */
+int tda_wasserstein_batched(const float* bdA, const int* nA, int nA_stride, int capA, int limA,
+                            const float* bdB, const int* nB, int nB_stride, int capB, int limB,
+                            const int* idxA, const int* idxB, long long B, double* out, void* stream);
+
 /* End-to-end host entry for the EEG feature path: host distance matrices in, host feature table
  * out (process_file_features, /root/reference/scripts/tda_eeg_classification_v2.py:338-442, for
  * R recordings x Bd bands x Wn windows at once).  D (R,Bd,Wn,N,N) float32 HOST.  Optional host

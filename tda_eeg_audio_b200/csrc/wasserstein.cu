@@ -1,0 +1,224 @@
+// wasserstein.cu — batched EXACT 1-Wasserstein distance between persistence diagrams
+// (L2 ground metric, Euclidean distance to the diagonal), float64.
+//
+// Replaces safe_wasserstein -> persim.wasserstein(dgm1, dgm2)
+//   /root/reference/scripts/utils.py:180-191 (alias at utils.py:12), called per window by
+//   /root/reference/scripts/tda_eeg_audio_comparison.py:95-96 and
+//   /root/reference/scripts/matched_vs_mismatched.py:87-95 (compute_cross_wasserstein).
+//
+// persim builds an (M+N)x(M+N) cost matrix (points x points, points x own diagonal copy, +inf
+// elsewhere, 0 diagonal-to-diagonal) and calls scipy's linear_sum_assignment.
+// That optimum equals  sum_j dt_j + min over assignments of the M points of S to either a point
+// of T (reduced cost c_ij - dt_j) or their own diagonal (cost ds_i): an M x (N+M) rectangular
+// assignment problem whose diagonal block is implicit.  One warp solves one pair with the
+// shortest-augmenting-path (Hungarian with potentials) algorithm: the M x N block of L2 costs
+// lives in the warp's shared memory in float64 (M <= N after an optional role swap), lanes stride
+// over the columns for the relax + arg-min step.  The optimum of an LSAP is unique in value, so
+// the result matches scipy's to rounding.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "tda_b200.h"
+
+namespace tda {
+namespace wasserstein {
+
+constexpr uint32_t kFull = 0xFFFFFFFFu;
+constexpr double kInf = 1e300;
+
+struct Params {
+    const float* bdA; const int* nA; int nA_stride, capA, limA;
+    const float* bdB; const int* nB; int nB_stride, capB, limB;
+    const int* idxA; const int* idxB;  // optional gather indices (pair k = A[idxA[k]] vs B[idxB[k]])
+    long long B;
+    double* out;
+    int rows_cap, cols_cap;  // min / max of the two caps (+1 for the placeholder point)
+};
+
+__host__ __device__ inline size_t smem_bytes(int rows_cap, int cols_cap) {
+    size_t s = 0;
+    s += (size_t)rows_cap * cols_cap * 8;          // cost block
+    s += (size_t)2 * (rows_cap + cols_cap) * 8;    // points S, T  (x, y)
+    s += (size_t)(rows_cap + cols_cap) * 8;        // ds, dt
+    s += (size_t)(rows_cap + 1) * 8;               // u
+    s += (size_t)2 * (rows_cap + cols_cap + 1) * 8; // v, minv
+    s += (size_t)2 * (rows_cap + cols_cap + 1) * 4; // p, way
+    return (s + 15) & ~(size_t)15;
+}
+
+// compact the finite rows of a diagram into (x, y) float64 pairs; empty -> one point (0,0)
+__device__ int load_diagram(const float* __restrict__ bd, int n, int cap, double* pts, int lane) {
+    if (n > cap) n = cap;
+    int m = 0;
+    const float2* rows = reinterpret_cast<const float2*>(bd);
+    for (int k0 = 0; k0 < n; k0 += 32) {
+        const int k = k0 + lane;
+        float2 r = make_float2(0.f, 0.f);
+        bool ok = false;
+        if (k < n) { r = rows[k]; ok = isfinite(r.x) && isfinite(r.y); }
+        const uint32_t bal = __ballot_sync(kFull, ok);
+        if (ok) {
+            const int pos = m + __popc(bal & ((1u << lane) - 1u));
+            pts[2 * pos] = (double)r.x;
+            pts[2 * pos + 1] = (double)r.y;
+        }
+        m += __popc(bal);
+    }
+    if (m == 0) {
+        if (lane == 0) { pts[0] = 0.0; pts[1] = 0.0; }
+        m = 1;
+    }
+    __syncwarp();
+    return m;
+}
+
+__global__ void __launch_bounds__(32) wasserstein_kernel(Params p) {
+    extern __shared__ __align__(16) unsigned char wsm[];
+    const int lane = threadIdx.x;
+    const int RC = p.rows_cap, CC = p.cols_cap;
+    double* cost = (double*)wsm;
+    double* PA = cost + (size_t)RC * CC;   // points of A, then points of B right behind them
+    double* dS = PA + 2 * (size_t)(RC + CC);
+    double* dT = dS + RC;
+    double* u = dT + CC;
+    double* v = u + (RC + 1);
+    double* minv = v + (RC + CC + 1);
+    int* pcol = (int*)(minv + (RC + CC + 1));
+    int* way = pcol + (RC + CC + 1);
+    const double cs = 0.7071067811865476, sn = 0.7071067811865475;  // np.cos(pi/4), np.sin(pi/4)
+
+    for (long long k = blockIdx.x; k < p.B; k += gridDim.x) {
+        const long long ia = p.idxA ? p.idxA[k] : k;
+        const long long ib = p.idxB ? p.idxB[k] : k;
+        // the diagram with fewer rows becomes S (rows of the assignment); the problem is symmetric
+        int na = p.nA[ia * p.nA_stride], nb = p.nB[ib * p.nB_stride];
+        double* S = PA;
+        double* T;
+        int M, N;
+        {
+            // load A then B into scratch, then order by size
+            int ma = load_diagram(p.bdA + ia * (long long)p.capA * 2, na, p.limA, PA, lane);
+            double* PB = PA + 2 * ma;
+            int mb = load_diagram(p.bdB + ib * (long long)p.capB * 2, nb, p.limB, PB, lane);
+            if (ma <= mb) { S = PA; T = PB; M = ma; N = mb; }
+            else { S = PB; T = PA; M = mb; N = ma; }
+        }
+        // distances to the diagonal: second coordinate after rotating by 45 degrees (persim)
+        for (int i = lane; i < M; i += 32) dS[i] = -S[2 * i] * sn + S[2 * i + 1] * cs;
+        for (int j = lane; j < N; j += 32) dT[j] = -T[2 * j] * sn + T[2 * j + 1] * cs;
+        __syncwarp();
+        // L2 costs with sklearn's Gram trick: sqrt(max(|s|^2 - 2 s.t + |t|^2, 0))
+        for (int e = lane; e < M * N; e += 32) {
+            const int i = e / N, j = e % N;
+            const double sx = S[2 * i], sy = S[2 * i + 1], tx = T[2 * j], ty = T[2 * j + 1];
+            const double ns = __dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy));
+            const double nt = __dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty));
+            const double dot = fma(sy, ty, __dmul_rn(sx, tx));
+            double d2 = __dadd_rn(__dadd_rn(__dmul_rn(-2.0, dot), ns), nt);
+            cost[(size_t)i * N + j] = sqrt(fmax(d2, 0.0));
+        }
+        const int Mc = N + M;  // columns: N real + M private diagonal columns
+        for (int j = lane; j <= Mc; j += 32) { v[j] = 0.0; pcol[j] = 0; }
+        for (int i = lane; i <= M; i += 32) u[i] = 0.0;
+        __syncwarp();
+        // ---- Hungarian with potentials (1-based rows/cols, column 0 is the virtual start)
+        for (int i = 1; i <= M; ++i) {
+            if (lane == 0) pcol[0] = i;
+            for (int j = lane; j <= Mc; j += 32) minv[j] = kInf;
+            // used[] as a bitmask in registers: lane owns columns j = lane + 32 t
+            uint32_t used = 0;  // bit t <-> column lane + 32 t   (Mc <= 32*32)
+            __syncwarp();
+            int j0 = 0;
+            while (true) {
+                if (lane == (j0 & 31)) used |= 1u << (j0 >> 5);
+                const int i0 = pcol[j0];
+                const double ui0 = u[i0];
+                double best = kInf;
+                int bestj = -1;
+                for (int j = lane, t = 0; j <= Mc; j += 32, ++t) {
+                    if (j == 0 || ((used >> t) & 1u)) continue;
+                    double a;
+                    if (j <= N) a = cost[(size_t)(i0 - 1) * N + (j - 1)] - dT[j - 1];
+                    else a = (j - N == i0) ? dS[i0 - 1] : kInf;
+                    const double cur = a - ui0 - v[j];
+                    double mv = minv[j];
+                    if (cur < mv) { mv = cur; minv[j] = cur; way[j] = j0; }
+                    if (mv < best) { best = mv; bestj = j; }
+                }
+                // warp arg-min (ties -> smaller column, deterministic)
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    const double ob = __shfl_xor_sync(kFull, best, o);
+                    const int oj = __shfl_xor_sync(kFull, bestj, o);
+                    if (ob < best || (ob == best && oj >= 0 && (bestj < 0 || oj < bestj))) { best = ob; bestj = oj; }
+                }
+                const double delta = best;
+                for (int j = lane, t = 0; j <= Mc; j += 32, ++t) {
+                    if ((used >> t) & 1u) { u[pcol[j]] += delta; v[j] -= delta; }
+                    else minv[j] -= delta;
+                }
+                __syncwarp();
+                j0 = bestj;
+                if (pcol[j0] == 0) break;
+            }
+            // augment along the path
+            if (lane == 0) {
+                int jj = j0;
+                while (jj) { const int j1 = way[jj]; pcol[jj] = pcol[j1]; jj = j1; }
+            }
+            __syncwarp();
+        }
+        // ---- total = matched costs + unmatched diagonal costs (persim: sum(D[match]))
+        double tot = 0.0;
+        for (int j = lane + 1; j <= Mc; j += 32) {
+            const int i = pcol[j];
+            if (j <= N) tot += (i > 0) ? cost[(size_t)(i - 1) * N + (j - 1)] : dT[j - 1];
+            else if (i > 0) tot += dS[i - 1];
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(kFull, tot, o);
+        if (lane == 0) p.out[k] = tot;
+        __syncwarp();
+    }
+}
+
+}  // namespace wasserstein
+}  // namespace tda
+
+extern "C" int tda_wasserstein_batched(const float* bdA, const int* nA, int nA_stride, int capA, int limA,
+                                       const float* bdB, const int* nB, int nB_stride, int capB, int limB,
+                                       const int* idxA, const int* idxB, long long B, double* out, void* stream) {
+    using namespace tda::wasserstein;
+    if (!bdA || !nA || !bdB || !nB || !out || B < 0 || capA < 0 || capB < 0 || nA_stride < 1 || nB_stride < 1)
+        return TDA_E_ARG;
+    if (B == 0) return 0;
+    Params p;
+    p.bdA = bdA; p.nA = nA; p.nA_stride = nA_stride; p.capA = capA;
+    p.bdB = bdB; p.nB = nB; p.nB_stride = nB_stride; p.capB = capB;
+    p.idxA = idxA; p.idxB = idxB; p.B = B; p.out = out;
+    if (limA <= 0 || limA > capA) limA = capA;
+    if (limB <= 0 || limB > capB) limB = capB;
+    p.limA = limA; p.limB = limB;
+    const int ca = limA < 1 ? 1 : limA, cb = limB < 1 ? 1 : limB;
+    p.rows_cap = ca < cb ? ca : cb;
+    p.cols_cap = ca < cb ? cb : ca;
+    if (p.rows_cap + p.cols_cap + 1 > 1024) return TDA_E_SIZE;
+    const size_t smem = smem_bytes(p.rows_cap, p.cols_cap);
+    if (smem > 227 * 1024) return TDA_E_SIZE;
+    cudaError_t e = cudaFuncSetAttribute(wasserstein_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 32) per_sm = 32;
+    long long grid = (long long)sms * per_sm;
+    if (grid > B) grid = B;
+    tda::ProfScope prof("wasserstein", (cudaStream_t)stream);
+    wasserstein_kernel<<<(int)grid, 32, smem, (cudaStream_t)stream>>>(p);
+    tda::count_launch();
+    return (int)cudaGetLastError();
+}

@@ -31,3 +31,82 @@ def eeg_features_from_distances(D, thresh=2.0, cap1=128, state=None, want_pairs=
 def check_truncation(result):
     """True if any window had more H1 bars than cap1 (one device->host sync)."""
     return bool((result["rips"]["status"] & 1).any().item())
+
+
+# ------------------------------------------------------------------------------------------------
+# audio side and the EEG-audio coupling (process_recording / matched_vs_mismatched)
+# ------------------------------------------------------------------------------------------------
+def select_windows(n_win, max_windows):
+    """tda_eeg_audio_comparison.py:77-80 / matched_vs_mismatched.py:52-55: evenly spaced subset."""
+    import numpy as np
+    if max_windows is not None and n_win > max_windows:
+        return np.linspace(0, n_win - 1, max_windows, dtype=int)
+    return np.arange(n_win)
+
+
+def audio_diagrams_from_envelope(env, fs=250, bands=None, window_sec=1.0, overlap=0.75, takens_dim=3,
+                                 subsample=2, max_windows=15, thresh=2.0, cap1=256, want_pairs=False):
+    """Envelope (R, T) CUDA float64 -> per band Takens/Rips diagrams of the selected windows.
+
+    The audio chain of process_recording (/root/reference/scripts/tda_eeg_audio_comparison.py:57-92)
+    ≡ get_audio_diagrams (/root/reference/scripts/matched_vs_mismatched.py:35-63) for R recordings:
+    ba band-pass filtfilt, 1 s windows (step int(win*(1-overlap))), evenly spaced window subset,
+    ONE tau per (recording, band) from the first selected window (max_lag = win//2), Takens(dim 3,
+    subsample), min-max normalisation, Rips H0/H1.
+    Returns dict: rips (diagram tensors over B = R*n_bands*n_sel items, item = (rec, band, sel)),
+    tau (R, n_bands) int32, idx (selected window indices), npts (B,), shape (R, n_bands, n_sel)."""
+    import numpy as np
+    import torch
+    from . import dsp, takens
+    from .rips import rips_h01_batched
+    bands = bands or dsp.FREQ_BANDS
+    names = list(bands)
+    R, T = env.shape
+    win = int(window_sec * fs)
+    step = int(win * (1 - overlap))
+    n_win = dsp.n_windows(T, win, step)
+    idx = select_windows(n_win, max_windows)
+    n_sel = len(idx)
+    ba = [dsp.design_bandpass_ba(*bands[b], fs) for b in names]
+    assert all(x is not None for x in ba), "degenerate band (lo >= hi)"
+    filt = dsp.filtfilt_batched(env, ba)                              # (n_bands, R, T)
+    starts = torch.from_numpy(idx * step).to(env.device)
+    gather = starts[:, None] + torch.arange(win, device=env.device)[None, :]        # (n_sel, win)
+    wins = filt[:, :, gather].permute(1, 0, 2, 3).contiguous()       # (R, n_bands, n_sel, win)
+    nb = len(names)
+    first = wins[:, :, 0, :].reshape(R * nb, win)
+    tau = takens.compute_tau_batched(first, max_lag=win // 2)        # one tau per (recording, band)
+    tau_items = tau.view(R, nb, 1).expand(R, nb, n_sel).reshape(-1).contiguous()
+    flat = wins.view(R * nb * n_sel, win)
+    ldp = (win + subsample - 1) // subsample
+    pts, npts = takens.takens_cloud_batched(flat, tau_items, takens_dim, subsample, normalise=True, ldp=ldp)
+    nmax = int(npts.max().item()) if npts.numel() else 0
+    nmax = max(nmax, 2)
+    D = takens.pairwise_distance_f32(pts[:, :nmax].contiguous(), npts, ld=nmax)
+    rips = rips_h01_batched(D, thresh=thresh, cap1=cap1, want_pairs=want_pairs, npts=npts, engine="medium")
+    return {"rips": rips, "tau": tau.view(R, nb), "idx": idx, "npts": npts, "shape": (R, nb, n_sel), "D": D}
+
+
+def cross_wasserstein(eeg_rips, audio_rips, idx_eeg=None, idx_audio=None):
+    """Per-item W_H0 and W_H1 between EEG and audio diagrams (safe_wasserstein semantics).
+    idx_* select which EEG / audio item forms pair k (None => same position)."""
+    from .wasserstein import wasserstein_batched
+    w0 = wasserstein_batched(eeg_rips["bd0"], eeg_rips["counts"][:, 0], audio_rips["bd0"],
+                             audio_rips["counts"][:, 0], idx_eeg, idx_audio)
+    w1 = wasserstein_batched(eeg_rips["bd1"], eeg_rips["counts"][:, 1], audio_rips["bd1"],
+                             audio_rips["counts"][:, 1], idx_eeg, idx_audio)
+    return w0, w1
+
+
+def mismatch_reference_recording(n_rec, n_subjects=45):
+    """SURVEY.md §8(d) config (d): recording r belongs to subject r % 45, condition (r // 45) % 2;
+    its mismatched audio is the subject's FIRST recording of the opposite condition
+    (/root/reference/scripts/matched_vs_mismatched.py:117-121).  Returns int array (n_rec,), -1 if
+    the subject has no recording in the other condition."""
+    import numpy as np
+    r = np.arange(n_rec)
+    subj, cond = r % n_subjects, (r // n_subjects) % 2
+    first = {}
+    for k in range(n_rec):
+        first.setdefault((int(subj[k]), int(cond[k])), k)
+    return np.array([first.get((int(subj[k]), 1 - int(cond[k])), -1) for k in range(n_rec)])

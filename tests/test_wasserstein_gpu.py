@@ -1,0 +1,63 @@
+"""GPU parity of the batched exact Wasserstein solver against persim's semantics on scipy's LSAP
+(oracle/wasserstein_ref.py).  Tolerance 1e-9 relative (north_star: 1e-5)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_dgm(rng, n, scale=1.0):
+    b = rng.random(n) * scale
+    return np.c_[b, b + rng.random(n) * scale * 0.5].astype(np.float32)
+
+
+def test_random_pairs(cuda):
+    import torch
+    from oracle import wasserstein_ref
+    from tda_eeg_audio_b200.wasserstein import wasserstein_batched
+    rng = np.random.default_rng(0)
+    capA, capB, K = 47, 124, 64
+    A = np.zeros((K, capA, 2), np.float32); B = np.zeros((K, capB, 2), np.float32)
+    nA = rng.integers(0, capA + 1, K).astype(np.int32); nB = rng.integers(0, capB + 1, K).astype(np.int32)
+    nA[:4] = [0, 0, 1, capA]; nB[:4] = [0, 5, 0, capB]
+    for k in range(K):
+        A[k, :nA[k]] = _rand_dgm(rng, nA[k]); B[k, :nB[k]] = _rand_dgm(rng, nB[k], 0.7)
+    A[5, 0, 1] = np.inf                              # essential bar: ignored
+    got = wasserstein_batched(torch.from_numpy(A).cuda(), torch.from_numpy(nA).cuda(),
+                              torch.from_numpy(B).cuda(), torch.from_numpy(nB).cuda()).cpu().numpy()
+    for k in range(K):
+        want = wasserstein_ref.safe_wasserstein(A[k, :nA[k]].astype(np.float64), B[k, :nB[k]].astype(np.float64))
+        assert abs(got[k] - want) <= 1e-9 * max(1.0, abs(want)), (k, got[k], want)
+
+
+def test_h0_like_and_index_pairing(cuda):
+    """H0 diagrams (all births 0) EEG 46 bars vs audio ~120 bars, matched and mismatched pairing."""
+    import torch
+    from oracle import wasserstein_ref
+    from tda_eeg_audio_b200.wasserstein import wasserstein_batched
+    rng = np.random.default_rng(1)
+    A = np.zeros((6, 47, 2), np.float32); B = np.zeros((4, 124, 2), np.float32)
+    for k in range(6):
+        A[k, :46, 1] = np.sort(rng.random(46)) * 1.4; A[k, 46] = (0, np.inf)
+    for k in range(4):
+        B[k, :119, 1] = np.sort(rng.random(119)) * 0.2; B[k, 119] = (0, np.inf)
+    nA = np.full(6, 47, np.int32); nB = np.full(4, 120, np.int32)
+    ia = np.array([0, 1, 2, 3, 4, 5, 0, 0], np.int32); ib = np.array([0, 1, 2, 3, 0, 1, 3, 2], np.int32)
+    got = wasserstein_batched(torch.from_numpy(A).cuda(), torch.from_numpy(nA).cuda(), torch.from_numpy(B).cuda(),
+                              torch.from_numpy(nB).cuda(), torch.from_numpy(ia).cuda(),
+                              torch.from_numpy(ib).cuda()).cpu().numpy()
+    for k in range(len(ia)):
+        want = wasserstein_ref.safe_wasserstein(A[ia[k], :47].astype(np.float64), B[ib[k], :120].astype(np.float64))
+        assert abs(got[k] - want) <= 1e-9 * max(1.0, abs(want))
+
+
+def test_properties_and_dropins(cuda):
+    from tda_eeg_audio_b200.wasserstein import safe_wasserstein, wasserstein
+    rng = np.random.default_rng(2)
+    d1, d2 = _rand_dgm(rng, 30), _rand_dgm(rng, 12)
+    assert wasserstein(d1, d1) == 0.0
+    assert abs(wasserstein(d1, d2) - wasserstein(d2, d1)) < 1e-12
+    lone = np.array([[0.2, 0.8]])
+    assert abs(wasserstein(lone, np.zeros((0, 2))) - 0.6 / np.sqrt(2)) < 1e-7     # to the diagonal
+    assert safe_wasserstein(np.array([[0.0, np.inf]]), np.array([[0.0, np.inf]])) == 0.0
+    assert safe_wasserstein(np.zeros(3), d2) == safe_wasserstein(np.zeros((0, 2)), d2)   # bad shape -> [[0,0]]
