@@ -7,23 +7,24 @@
 // B200-first design (not a port of Ripser's heap-based column reduction):
 //   * one WARP owns one window; a CTA is a bundle of independent warps, the grid is sized in
 //     multiples of the SM count and every warp strides over the batch.  All state of a window
-//     lives in that warp's slice of shared memory (~18 KB for N=47) — the distance matrix is
-//     read from HBM exactly once, coalesced by rows, and the diagrams are written exactly once.
+//     lives in that warp's ~18 KB slice of shared memory — the distance matrix is read from HBM
+//     exactly once, coalesced by rows, and the diagrams are written exactly once.
 //   * filtration = per-warp stable LSD radix sort (4 x 8 bit, __match_any_sync ranking) of the
 //     order-preserving integer image of the float32 edge lengths; initial order is descending
 //     edge index so stability gives Ripser's tie-break (equal length => larger index first).
-//   * H0 and H1 come out of ONE sweep over the sorted edges.  H0 is Kruskal with warp-parallel
-//     relabelling.  H1 is persistent cohomology by cocycle annotation: every live 1-cocycle is a
-//     bit ("slot") in a W-word mask stored per edge (PHI[edge]); adj[v] holds the neighbours of v
-//     so far as a 64-bit mask.  For a cycle-creating edge (i,j) the apexes of the triangles that
-//     enter with it are G = adj[i] & adj[j]; lanes take one apex each and evaluate the coboundary
-//     of *all* live cocycles on that triangle with two XORs.  Apparent (zero-persistence) pairs
-//     cost nothing; only the ~30 real classes of a window ever allocate a slot.  See
-//     oracle/pcoh_model.py for the executable statement and its proof-by-test against the
-//     definition-level reduction.
+//   * H0 = Kruskal over the sorted edges, 32 edges checked per step, warp-parallel relabelling.
+//   * the sorted ranks are scattered into a rank matrix T[i][v] (u16).  "Apex v closes a triangle
+//     over edge (i,j) of rank r" is then max(T[i][v], T[j][v]) < r: no adjacency to maintain, and
+//     one packed-u16 min/max pass over T decides for EVERY edge in parallel whether it has an
+//     apex at its own time — the edges that do not are the births of real H1 classes.
+//   * H1 = persistent cohomology by cocycle annotation (oracle/pcoh_model.py is the executable
+//     statement): every live 1-cocycle is a bit ("slot") of a W-word mask stored per edge,
+//     PHI[rank].  The serial sweep only runs through the LIVE SPANS (from a birth until no class is
+//     alive); lanes are apexes, so the coboundary of ALL live cocycles on a triangle is two XORs
+//     per lane.  Apparent (zero-persistence) pairs cost nothing and take no slot.
 //   * tie runs (equal float32 lengths) are replayed in the exact simplexwise order (all edges of
-//     the run, then the run's triangles in descending index) so that the persistence PAIRS, not
-//     only the diagrams, are bit-identical to Ripser's.
+//     the run, then the run's triangles in descending index, apparent pairs recognised inside the
+//     run) so that the persistence PAIRS, not only the diagrams, are bit-identical to Ripser's.
 //   * capacity tiers: W=2 (64 simultaneous classes, shared memory) -> W=4 -> W=64 with PHI in a
 //     global scratch; a window that exceeds a tier is pushed on a device-side list and redone by
 //     the next tier, no host round-trip.
@@ -39,6 +40,8 @@ namespace rips_small {
 constexpr int kMaxN = 64;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 constexpr uint32_t kEssential = 0xFFFFFFFFu;
+constexpr uint32_t kMst = 0x4000u;   // P flag: edge merges two components (H0 death)
+constexpr uint32_t kTie = 0x8000u;   // P flag: the next edge in the order has the same length
 
 struct Params {
     const float* D;
@@ -57,7 +60,8 @@ struct Params {
     int* overflow_list;    // nullptr on the last tier
     int* n_overflow;
     uint32_t* phi_global;  // per-warp PHI scratch (PHI_GLOBAL tiers), E*W words per warp
-    uint32_t* rec_global;  // per-warp record scratch (PHI_GLOBAL tiers), 3*R words per warp
+    uint32_t* rec_global;  // per-warp record scratch (PHI_GLOBAL tiers), 4*R words per warp
+    uint8_t* defv_global;  // per-warp tie-run scratch, Epad bytes per warp (all tiers)
 };
 
 __host__ __device__ inline int c2(int i) { return i * (i - 1) / 2; }
@@ -66,24 +70,25 @@ __host__ __device__ inline int c3(int i) { return i * (i - 1) * (i - 2) / 6; }
 template <int W, bool PHI_GLOBAL> struct Layout {
     // all sizes in bytes, per warp
     static __host__ __device__ int epad(int N) { return (c2(N) + 31) & ~31; }
-    static __host__ __device__ int recs(int N) { return PHI_GLOBAL ? c2(N) + 64 : 64 * W; }
-    static __host__ __device__ size_t region1(int N) {
-        size_t sortb = (size_t)epad(N) * 6;
-        size_t phib = PHI_GLOBAL ? 0 : (size_t)c2(N) * W * 4;
-        size_t r = sortb > phib ? sortb : phib;
-        return (r + 15) & ~(size_t)15;
+    static __host__ __device__ int ldt(int N) { return ((((N + 1) / 2) | 1) * 2); }  // u16 per T row, odd #words
+    static __host__ __device__ int recs(int N) { return PHI_GLOBAL ? c2(N) + 64 : 48 * W; }
+    static __host__ __device__ size_t a16(size_t x) { return (x + 15) & ~(size_t)15; }
+    static __host__ __device__ size_t region_a(int N) {      // sort keys + histogram | rank matrix T
+        size_t s1 = (size_t)epad(N) * 4 + 1024, s2 = (size_t)N * ldt(N) * 2;
+        return a16(s1 > s2 ? s1 : s2);
+    }
+    static __host__ __device__ size_t region_c(int N) {      // sort ping-pong | PHI
+        size_t s1 = (size_t)epad(N) * 6, s2 = PHI_GLOBAL ? 0 : (size_t)c2(N) * W * 4;
+        return a16(s1 > s2 ? s1 : s2);
     }
     static __host__ __device__ size_t bytes(int N) {
-        size_t s = 0;
-        s += 2 * kMaxN * 8;                                   // adj, runadj
-        s += (size_t)epad(N) * 4;                             // K
-        s += region1(N);                                      // sort ping-pong | PHI
-        s += 256 * 4;                                         // radix histogram
-        s += PHI_GLOBAL ? 0 : (size_t)recs(N) * 12;           // death records
-        s += (size_t)epad(N) * 2;                             // P
-        s += (size_t)32 * W * 2;                              // brank
+        size_t s = region_a(N) + region_c(N);
+        s += a16((size_t)epad(N) * 2);                        // P
+        s += PHI_GLOBAL ? 0 : (size_t)recs(N) * 16;           // death records
+        s += (size_t)epad(N) / 8;                             // visit bitmap
+        s += 32 * W * 4 + 32 * W * 2;                         // bkey, brank
         s += 2 * kMaxN;                                       // comp, eld
-        return (s + 15) & ~(size_t)15;
+        return a16(s);
     }
 };
 
@@ -92,7 +97,6 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
 }
-
 __device__ __forceinline__ uint32_t float_key(float d) {
     uint32_t u = __float_as_uint(d);
     return (u >> 31) ? ~u : (u | 0x80000000u);
@@ -101,34 +105,37 @@ __device__ __forceinline__ float key_float(uint32_t k) {
     uint32_t u = (k >> 31) ? (k & 0x7FFFFFFFu) : ~k;
     return __uint_as_float(u);
 }
-
-// combinatorial index of triangle {i, j, v}, i > j, v distinct
-__device__ __forceinline__ int tri_index(int i, int j, int v) {
-    if (v > i) return c3(v) + c2(i) + j;
-    if (v > j) return c3(i) + c2(v) + j;
-    return c3(i) + c2(j) + v;
+__device__ __forceinline__ int tri_index(int x, int y, int z) {
+    const int a = max(x, max(y, z)), c = min(x, min(y, z)), b = x + y + z - a - c;
+    return c3(a) + c2(b) + c;
 }
-__device__ __forceinline__ int edge_q(int a, int b) { return a > b ? c2(a) + b : c2(b) + a; }
 
 template <int W, bool PHI_GLOBAL> struct Warp {
     // ---- per-warp storage
-    unsigned long long* adj;
-    unsigned long long* runadj;
-    uint32_t* K;
-    uint32_t* R1;  // region1: sort ping-pong, then PHI (shared tiers)
-    uint32_t* hist;
-    uint32_t* rec;  // [3][R]: birth rank, death key, death triangle
-    uint16_t* P;
-    uint16_t* brank;
+    uint32_t* K;      // region A during the sort
+    uint32_t* hist;   // region A, behind K
+    uint16_t* T;      // region A after Kruskal: rank matrix, row stride ldt
+    uint32_t* K2;     // region C during the sort
+    uint16_t* P2;
+    uint32_t* phi;    // region C afterwards (or global): PHI[rank][W]
+    uint16_t* P;      // (i << 8 | j) | flags, by rank
+    uint32_t* rec;    // [4][R]: birth rank, birth key, death key, death triangle
+    uint32_t* visit;  // bitmap over ranks: a real class may be born here
+    uint32_t* bkey;   // per slot: key of the birth edge
+    uint16_t* brank;  // per slot: rank of the birth edge
     uint8_t* comp;
     uint8_t* eld;
-    uint32_t* phi;
-    int lane, N, E, Epad, R;
+    uint8_t* defv;    // tie runs only (global scratch): defining apex of an apparent run edge
+    const float* Db;
+    int lane, N, E, Epad, R, ldt, ld;
     // ---- per-window uniform state
     uint32_t live[W], used[W];
     int n0, n1, ncomp, m;
     bool overflow;
 
+    __device__ __forceinline__ float dist(int a, int b) const {
+        return __ldg(Db + (size_t)min(a, b) * ld + max(a, b)) + 0.0f;
+    }
     __device__ __forceinline__ bool live_any() const {
         uint32_t a = 0;
 #pragma unroll
@@ -137,7 +144,7 @@ template <int W, bool PHI_GLOBAL> struct Warp {
     }
 
     // ------------------------------------------------------------------ slots
-    __device__ int alloc_slot() {
+    __device__ __forceinline__ int alloc_slot(int upto) {
         for (int attempt = 0; attempt < 2; ++attempt) {
 #pragma unroll
             for (int w = 0; w < W; ++w) {
@@ -151,7 +158,7 @@ template <int W, bool PHI_GLOBAL> struct Warp {
             }
             // every slot has been used once: scrub the dead bits out of PHI and recycle
             __syncwarp();
-            for (int q = lane; q < E; q += 32) {
+            for (int q = lane; q < upto; q += 32) {
 #pragma unroll
                 for (int w = 0; w < W; ++w) phi[(size_t)q * W + w] &= live[w];
             }
@@ -167,67 +174,33 @@ template <int W, bool PHI_GLOBAL> struct Warp {
         overflow = true;
         return -1;
     }
-
-    __device__ __forceinline__ void phi_store_uniform(int q, const uint32_t (&v)[W]) {
+    __device__ __forceinline__ void birth(int r, int upto, uint32_t key) {
+        const int s = alloc_slot(upto);
+        if (s < 0) return;
         if (lane == 0) {
+            brank[s] = (uint16_t)r;
+            bkey[s] = key;
 #pragma unroll
-            for (int w = 0; w < W; ++w) phi[(size_t)q * W + w] = v[w];
-        }
-    }
-
-    // ------------------------------------------------------------------ H0 step
-    // returns true when edge (i,j) merges two components (emits the H0 pair)
-    __device__ bool h0_step(const Params& p, int b, int i, int j, uint32_t key) {
-        if (ncomp <= 1) return false;
-        int ci = comp[i], cj = comp[j];
-        if (ci == cj) return false;
-        int ei = eld[ci], ej = eld[cj];
-        float d = key_float(key);
-        if (d != 0.0f) {
-            if (lane == 0) {
-                size_t o = ((size_t)b * N + n0) * 2;
-                p.bd0[o] = 0.0f;
-                p.bd0[o + 1] = d;
-                if (p.pr0) {
-                    p.pr0[o] = min(ei, ej);
-                    p.pr0[o + 1] = c2(i) + j;
-                }
-            }
-            ++n0;
+            for (int w = 0; w < W; ++w) phi[(size_t)r * W + w] = (w == (s >> 5)) ? (1u << (s & 31)) : 0u;
         }
         __syncwarp();
-        for (int v = lane; v < N; v += 32)
-            if (comp[v] == ci) comp[v] = (uint8_t)cj;
-        if (lane == 0) eld[cj] = (uint8_t)max(ei, ej);
-        __syncwarp();
-        --ncomp;
-        return true;
-    }
-
-    __device__ __forceinline__ void add_adj(int i, int j, bool run) {
-        if (lane == 0) {
-            adj[i] |= 1ull << j;
-            adj[j] |= 1ull << i;
-            if (run) {
-                runadj[i] |= 1ull << j;
-                runadj[j] |= 1ull << i;
-            }
-        }
     }
 
     // ------------------------------------------------------------------ deaths inside a group
-    // c[h] = coboundary masks of the live cocycles on triangle (i, j, v = lane + 32 h)
-    __device__ void resolve(int i, int j, uint32_t key, uint32_t (&c)[2][W]) {
+    // c[h] = coboundary masks of the live cocycles on triangle (a, b, v = lane + 32 h); lanes with
+    // isdef[h] carry the value of an apparent run edge they define (updated linearly, never a death)
+    __device__ __forceinline__ void resolve(int a, int b, uint32_t curkey, int upto, uint32_t (&c)[2][W],
+                                            const bool (&isdef)[2]) {
         while (true) {
             uint32_t any0 = 0, any1 = 0;
 #pragma unroll
             for (int w = 0; w < W; ++w) { any0 |= c[0][w]; any1 |= c[1][w]; }
-            uint32_t nz1 = __ballot_sync(kFull, any1 != 0);
-            uint32_t nz0 = __ballot_sync(kFull, any0 != 0);
+            const uint32_t nz1 = __ballot_sync(kFull, any1 != 0 && !isdef[1]);
+            const uint32_t nz0 = __ballot_sync(kFull, any0 != 0 && !isdef[0]);
             if (!(nz0 | nz1)) return;
-            int h = nz1 ? 1 : 0;
-            int src = 31 - __clz(nz1 ? nz1 : nz0);
-            int v = src + 32 * h;
+            const int h = nz1 ? 1 : 0;
+            const int src = 31 - __clz(nz1 ? nz1 : nz0);
+            const int v = src + 32 * h;
             uint32_t cv[W];
 #pragma unroll
             for (int w = 0; w < W; ++w) cv[w] = __shfl_sync(kFull, h ? c[1][w] : c[0][w], src);
@@ -237,20 +210,22 @@ template <int W, bool PHI_GLOBAL> struct Warp {
             for (int w = 0; w < W; ++w) {
                 uint32_t bits = cv[w];
                 while (bits) {
-                    int s = __ffs(bits) - 1;
+                    const int s = __ffs(bits) - 1;
                     bits &= bits - 1;
-                    int a = brank[32 * w + s];
-                    if (a > age) { age = a; slot = 32 * w + s; }
+                    const int ag = brank[32 * w + s];
+                    if (ag > age) { age = ag; slot = 32 * w + s; }
                 }
             }
             const int sw = slot >> 5;
             const uint32_t sb = 1u << (slot & 31);
-            if (K[age] != key) {  // non-zero persistence: keep a record
+            const uint32_t bk = bkey[slot];
+            if (bk != curkey) {  // non-zero persistence: keep a record
                 if (n1 < R) {
                     if (lane == 0) {
                         rec[n1] = (uint32_t)age;
-                        rec[R + n1] = key;
-                        rec[2 * R + n1] = (uint32_t)tri_index(i, j, v);
+                        rec[R + n1] = bk;
+                        rec[2 * R + n1] = curkey;
+                        rec[3 * R + n1] = (uint32_t)tri_index(a, b, v);
                     }
                     ++n1;
                 } else {
@@ -277,7 +252,7 @@ template <int W, bool PHI_GLOBAL> struct Warp {
             }
             if (absorb) {
                 __syncwarp();
-                for (int q = lane; q < E; q += 32) {
+                for (int q = lane; q < upto; q += 32) {
                     uint32_t* e = phi + (size_t)q * W;
                     if (e[sw] & sb) {
 #pragma unroll
@@ -289,145 +264,193 @@ template <int W, bool PHI_GLOBAL> struct Warp {
         }
     }
 
-    // evaluate the triangles (i, j, v), v in G, against PHI as it stands and resolve deaths
-    __device__ void group_eval(int i, int j, unsigned long long G, uint32_t key) {
-        uint32_t c[2][W];
-        const int q = c2(i) + j;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            int v = lane + 32 * h;
-            bool in = (G >> v) & 1ull;
-#pragma unroll
-            for (int w = 0; w < W; ++w) c[h][w] = 0;
-            if (in) {
-                const uint32_t* pe = phi + (size_t)q * W;
-                const uint32_t* pa = phi + (size_t)edge_q(i, v) * W;
-                const uint32_t* pb = phi + (size_t)edge_q(j, v) * W;
-#pragma unroll
-                for (int w = 0; w < W; ++w) c[h][w] = (pe[w] ^ pa[w] ^ pb[w]) & live[w];
-            }
-        }
-        resolve(i, j, key, c);
-    }
-
     // ------------------------------------------------------------------ one single (untied) edge
-    __device__ void fast_edge(const Params& p, int b, int r, uint32_t key) {
-        const int pij = P[r];
-        const int i = pij >> 8, j = pij & 255;
-        const int q = c2(i) + j;
-        const bool merging = h0_step(p, b, i, j, key);
-        const unsigned long long G = adj[i] & adj[j];
-        __syncwarp();
-        add_adj(i, j, false);
-        uint32_t zero[W];
-#pragma unroll
-        for (int w = 0; w < W; ++w) zero[w] = 0;
-        if (merging) { phi_store_uniform(q, zero); __syncwarp(); return; }
-        if (G == 0) {  // a real class is born
-            int s = alloc_slot();
-            if (s < 0) return;
-            if (lane == 0) brank[s] = (uint16_t)r;
-#pragma unroll
-            for (int w = 0; w < W; ++w) zero[w] = (w == (s >> 5)) ? (1u << (s & 31)) : 0u;
-            phi_store_uniform(q, zero);
-            __syncwarp();
+    __device__ __forceinline__ void single_edge(int r) {
+        const uint32_t pij = P[r];
+        if (pij & kMst) return;  // PHI[r] stays 0: live cocycles extend by 0 over a merging edge
+        const int i = (pij >> 8) & 63, j = pij & 255;
+        const uint16_t* Ti = T + i * ldt;
+        const uint16_t* Tj = T + j * ldt;
+        const int v1 = lane + 32;
+        uint32_t ta[2], tb[2];
+        ta[0] = 0xFFFFu; tb[0] = 0xFFFFu;
+        ta[1] = 0xFFFFu; tb[1] = 0xFFFFu;
+        if (lane < N) { ta[0] = Ti[lane]; tb[0] = Tj[lane]; }
+        if (v1 < N) { ta[1] = Ti[v1]; tb[1] = Tj[v1]; }
+        bool in[2];
+        in[0] = ta[0] < (uint32_t)r && tb[0] < (uint32_t)r;
+        in[1] = ta[1] < (uint32_t)r && tb[1] < (uint32_t)r;
+        const uint32_t G0 = __ballot_sync(kFull, in[0]);
+        const uint32_t G1 = __ballot_sync(kFull, in[1]);
+        if (!(G0 | G1)) {  // no apex yet: a real class is born
+            birth(r, r, float_key(dist(i, j)));
             return;
         }
-        if (!live_any()) { phi_store_uniform(q, zero); __syncwarp(); return; }
-        // apparent pair (e, top triangle); extend every live cocycle over e and test the others
-        const int vtop = 63 - __clzll(G);
+        if (!live_any()) return;
+        // apparent pair (e, top triangle): extend every live cocycle over e, test the other apexes
         uint32_t c[2][W];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            int v = lane + 32 * h;
-            bool in = (G >> v) & 1ull;
 #pragma unroll
             for (int w = 0; w < W; ++w) c[h][w] = 0;
-            if (in) {
-                const uint32_t* pa = phi + (size_t)edge_q(i, v) * W;
-                const uint32_t* pb = phi + (size_t)edge_q(j, v) * W;
+            if (in[h]) {
+                const uint32_t* pa = phi + (size_t)ta[h] * W;
+                const uint32_t* pb = phi + (size_t)tb[h] * W;
 #pragma unroll
                 for (int w = 0; w < W; ++w) c[h][w] = pa[w] ^ pb[w];
             }
         }
+        const int vtop = G1 ? 63 - __clz(G1) : 31 - __clz(G0);
         uint32_t xtop[W];
 #pragma unroll
         for (int w = 0; w < W; ++w)
             xtop[w] = __shfl_sync(kFull, (vtop >> 5) ? c[1][w] : c[0][w], vtop & 31) & live[w];
-        phi_store_uniform(q, xtop);
+        if (lane == 0) {
+#pragma unroll
+            for (int w = 0; w < W; ++w) phi[(size_t)r * W + w] = xtop[w];
+        }
         uint32_t anyc = 0;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            int v = lane + 32 * h;
-            bool in = ((G >> v) & 1ull) && v != vtop;
+            const bool use = in[h] && (lane + 32 * h) != vtop;
 #pragma unroll
             for (int w = 0; w < W; ++w) {
-                c[h][w] = in ? ((c[h][w] ^ xtop[w]) & live[w]) : 0u;
+                c[h][w] = use ? ((c[h][w] ^ xtop[w]) & live[w]) : 0u;
                 anyc |= c[h][w];
             }
         }
         __syncwarp();
-        if (__ballot_sync(kFull, anyc != 0)) resolve(i, j, key, c);
+        if (__ballot_sync(kFull, anyc != 0)) {
+            const bool nodef[2] = {false, false};
+            resolve(i, j, float_key(dist(i, j)), r + 1, c, nodef);
+        }
     }
 
     // ------------------------------------------------------------------ a run of equal-length edges
-    __device__ void tie_run(const Params& p, int b, int r, int r1, uint32_t key) {
-        for (int v = lane; v < N; v += 32) runadj[v] = 0;
-        __syncwarp();
-        for (int pidx = r; pidx < r1; ++pidx) {
-            const int pij = P[pidx];
-            const int i = pij >> 8, j = pij & 255;
-            const int q = c2(i) + j;
-            const bool merging = h0_step(p, b, i, j, key);
-            uint32_t val[W];
+    // triangles (a, b, v), v < b < a, v in (G0, G1); vdef >= 0: (a,b) is an apparent run edge defined
+    // by apex vdef (the top of G)
+    __device__ __forceinline__ void run_group(int a, int b, int rab, uint32_t G0, uint32_t G1, int vdef,
+                                              int r0, int r1, uint32_t curkey) {
+        const uint16_t* Ta = T + a * ldt;
+        const uint16_t* Tb = T + b * ldt;
+        uint32_t pe[W];
+        if (vdef >= 0) {
+            const uint32_t* x = phi + (size_t)Ta[vdef] * W;
+            const uint32_t* y = phi + (size_t)Tb[vdef] * W;
 #pragma unroll
-            for (int w = 0; w < W; ++w) val[w] = 0;
-            if (!merging) {
-                int s = alloc_slot();
-                if (s < 0) return;
-                if (lane == 0) brank[s] = (uint16_t)pidx;
+            for (int w = 0; w < W; ++w) pe[w] = (x[w] ^ y[w]) & live[w];
+            if (lane == 0) {
 #pragma unroll
-                for (int w = 0; w < W; ++w) val[w] = (w == (s >> 5)) ? (1u << (s & 31)) : 0u;
+                for (int w = 0; w < W; ++w) phi[(size_t)rab * W + w] = pe[w];
             }
-            phi_store_uniform(q, val);
-            add_adj(i, j, true);
-            __syncwarp();
-        }
-        if (!live_any()) return;
-        // the run's triangles in descending index order: (a desc, b desc, c desc), a > b > c
-        for (int a = N - 1; a >= 2; --a) {
-            const unsigned long long adj_a = adj[a], run_a = runadj[a];
-            const unsigned long long Pa = adj_a & ((1ull << a) - 1ull);
-            if (Pa == 0) continue;
-            unsigned long long mk[2];
+        } else {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                int bb = lane + 32 * h;
-                mk[h] = 0;
-                if (bb < a && ((Pa >> bb) & 1ull)) {
-                    unsigned long long cand = adj_a & adj[bb] & ((1ull << bb) - 1ull);
-                    if (!((run_a >> bb) & 1ull)) cand &= (run_a | runadj[bb]);
-                    mk[h] = cand;
+            for (int w = 0; w < W; ++w) pe[w] = phi[(size_t)rab * W + w];
+        }
+        uint32_t c[2][W];
+        bool isdef[2] = {false, false};
+        int defq[2] = {-1, -1};
+        uint32_t anyc = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int v = lane + 32 * h;
+            const bool in = ((h ? G1 : G0) >> lane) & 1u;
+#pragma unroll
+            for (int w = 0; w < W; ++w) c[h][w] = 0;
+            if (in && v != vdef) {
+                const int ra = Ta[v], rb = Tb[v];
+                const uint32_t* x = phi + (size_t)ra * W;
+                const uint32_t* y = phi + (size_t)rb * W;
+#pragma unroll
+                for (int w = 0; w < W; ++w) c[h][w] = (pe[w] ^ x[w] ^ y[w]) & live[w];
+                if (ra >= r0 && defv[ra - r0] == b) { isdef[h] = true; defq[h] = ra; }
+                else if (rb >= r0 && defv[rb - r0] == a) { isdef[h] = true; defq[h] = rb; }
+                if (!isdef[h]) {
+#pragma unroll
+                    for (int w = 0; w < W; ++w) anyc |= c[h][w];
                 }
             }
-            for (int h = 1; h >= 0; --h) {
-                uint32_t bits = __ballot_sync(kFull, mk[h] != 0);
+        }
+        __syncwarp();
+        if (__ballot_sync(kFull, anyc != 0)) resolve(a, b, curkey, r1, c, isdef);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (isdef[h]) {
+#pragma unroll
+                for (int w = 0; w < W; ++w) phi[(size_t)defq[h] * W + w] = c[h][w] & live[w];
+            }
+        }
+        __syncwarp();
+    }
+
+    __device__ __forceinline__ void tie_run(int r0, int r1) {
+        const uint32_t p0 = P[r0];
+        const uint32_t curkey = float_key(dist((p0 >> 8) & 63, p0 & 255));
+        // pass 1 (rank order): apparent pairs inside the run take no slot.  A cycle-creating run edge
+        // is apparent iff its first cofacet (largest apex among the triangles present once the whole
+        // run has entered) has it as youngest edge.
+        for (int pr = r0; pr < r1 && !overflow; ++pr) {
+            const uint32_t pij = P[pr];
+            uint8_t dv = 254;  // merging edge
+            if (!(pij & kMst)) {
+                const int i = (pij >> 8) & 63, j = pij & 255;
+                const uint16_t* Ti = T + i * ldt;
+                const uint16_t* Tj = T + j * ldt;
+                const int v1 = lane + 32;
+                const bool in0 = lane < N && Ti[lane] < r1 && Tj[lane] < r1;
+                const bool in1 = v1 < N && Ti[v1] < r1 && Tj[v1] < r1;
+                const uint32_t G0 = __ballot_sync(kFull, in0), G1 = __ballot_sync(kFull, in1);
+                dv = 255;
+                if (G0 | G1) {
+                    const int vt = G1 ? 63 - __clz(G1) : 31 - __clz(G0);
+                    if (Ti[vt] < pr && Tj[vt] < pr) dv = (uint8_t)vt;
+                }
+                if (dv == 255) birth(pr, r1, curkey);
+            }
+            if (lane == 0) defv[pr - r0] = dv;
+        }
+        __syncwarp();
+        if (overflow || !live_any()) return;
+        // pass 2: the run's triangles in descending index: a desc, b desc, apex c desc (c < b < a)
+        for (int a = N - 1; a >= 2; --a) {
+            const uint16_t* Ta = T + a * ldt;
+            const int vb1 = lane + 32;
+            const uint32_t B0 = __ballot_sync(kFull, lane < a && Ta[lane] < r1);
+            const uint32_t B1 = __ballot_sync(kFull, vb1 < a && Ta[vb1] < r1);
+            for (int hb = 1; hb >= 0; --hb) {
+                uint32_t bits = hb ? B1 : B0;
                 while (bits) {
-                    int src = 31 - __clz(bits);
-                    bits &= ~(1u << src);
-                    unsigned long long Gm = __shfl_sync(kFull, mk[h], src);
-                    group_eval(a, src + 32 * h, Gm, key);
-                    if (overflow) return;
-                    if (!live_any()) return;
+                    const int bb = 32 * hb + 31 - __clz(bits);
+                    bits &= ~(1u << (bb & 31));
+                    const uint16_t* Tb = T + bb * ldt;
+                    const int rab = Ta[bb];
+                    const bool ab_run = rab >= r0;
+                    bool in[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int v = lane + 32 * h;
+                        in[h] = false;
+                        if (v < bb) {
+                            const int ra = Ta[v], rb = Tb[v];
+                            in[h] = ra < r1 && rb < r1 && (ab_run || ra >= r0 || rb >= r0);
+                        }
+                    }
+                    const uint32_t G0 = __ballot_sync(kFull, in[0]), G1 = __ballot_sync(kFull, in[1]);
+                    if (!(G0 | G1)) continue;
+                    int vdef = -1;
+                    if (ab_run) {
+                        const int dv = defv[rab - r0];
+                        if (dv < 254 && dv < bb) vdef = dv;
+                    }
+                    run_group(a, bb, rab, G0, G1, vdef, r0, r1, curkey);
+                    if (overflow || !live_any()) return;
                 }
             }
         }
     }
 
     // ------------------------------------------------------------------ radix sort of (K, P)
-    __device__ void sort_edges() {
-        uint32_t* K2 = R1;
-        uint16_t* P2 = (uint16_t*)(R1 + Epad);
+    __device__ __forceinline__ void sort_edges() {
         uint32_t* srcK = K; uint16_t* srcP = P;
         uint32_t* dstK = K2; uint16_t* dstP = P2;
         const uint32_t lt = lanemask_lt();
@@ -437,19 +460,18 @@ template <int W, bool PHI_GLOBAL> struct Warp {
             for (int t = 0; t < 8; ++t) hist[lane + 32 * t] = 0;
             __syncwarp();
             for (int k0 = 0; k0 < Epad; k0 += 32) {
-                uint32_t dg = (srcK[k0 + lane] >> shift) & 255u;
-                uint32_t peers = __match_any_sync(kFull, dg);
+                const uint32_t dg = (srcK[k0 + lane] >> shift) & 255u;
+                const uint32_t peers = __match_any_sync(kFull, dg);
                 if ((peers & lt) == 0) hist[dg] += __popc(peers);
                 __syncwarp();
             }
-            // exclusive scan of the 256 bins (8 per lane)
             uint32_t loc[8], sum = 0;
 #pragma unroll
             for (int t = 0; t < 8; ++t) { loc[t] = hist[lane * 8 + t]; sum += loc[t]; }
             uint32_t incl = sum;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                uint32_t y = __shfl_up_sync(kFull, incl, o);
+                const uint32_t y = __shfl_up_sync(kFull, incl, o);
                 if (lane >= o) incl += y;
             }
             uint32_t run = incl - sum;
@@ -458,11 +480,11 @@ template <int W, bool PHI_GLOBAL> struct Warp {
             for (int t = 0; t < 8; ++t) { hist[lane * 8 + t] = run; run += loc[t]; }
             __syncwarp();
             for (int k0 = 0; k0 < Epad; k0 += 32) {
-                uint32_t key = srcK[k0 + lane];
-                uint16_t pay = srcP[k0 + lane];
-                uint32_t dg = (key >> shift) & 255u;
-                uint32_t peers = __match_any_sync(kFull, dg);
-                uint32_t pos = hist[dg] + __popc(peers & lt);
+                const uint32_t key = srcK[k0 + lane];
+                const uint16_t pay = srcP[k0 + lane];
+                const uint32_t dg = (key >> shift) & 255u;
+                const uint32_t peers = __match_any_sync(kFull, dg);
+                const uint32_t pos = hist[dg] + __popc(peers & lt);
                 __syncwarp();
                 dstK[pos] = key;
                 dstP[pos] = pay;
@@ -472,12 +494,11 @@ template <int W, bool PHI_GLOBAL> struct Warp {
             uint32_t* tk = srcK; srcK = dstK; dstK = tk;
             uint16_t* tp = srcP; srcP = dstP; dstP = tp;
         }
-        // 4 passes: result is back in (K, P)
     }
 
     // ------------------------------------------------------------------ one window
-    __device__ void run(const Params& p, int b) {
-        const float* Db = p.D + (size_t)b * p.strideB;
+    __device__ __forceinline__ void run(const Params& p, int b) {
+        Db = p.D + (size_t)b * p.strideB;
         overflow = false;
         n0 = n1 = 0;
         ncomp = N;
@@ -488,20 +509,16 @@ template <int W, bool PHI_GLOBAL> struct Warp {
         for (int k = E + lane; k < Epad; k += 32) { K[k] = 0xFFFFFFFFu; P[k] = 0; }
         for (int row = 0; row < N - 1; ++row) {
             for (int i = row + 1 + lane; i < N; i += 32) {
-                float d = __ldg(Db + (size_t)row * p.ld + i) + 0.0f;
-                bool ok = d <= p.thresh;
+                const float d = __ldg(Db + (size_t)row * ld + i) + 0.0f;
+                const bool ok = d <= p.thresh;
                 nan_seen |= (d != d);
-                int k = E - 1 - (c2(i) + row);
+                const int k = E - 1 - (c2(i) + row);
                 K[k] = ok ? float_key(d) : 0xFFFFFFFFu;
                 P[k] = (uint16_t)((i << 8) | row);
                 valid += ok;
             }
         }
-        for (int v = lane; v < N; v += 32) {
-            adj[v] = 0;
-            comp[v] = (uint8_t)v;
-            eld[v] = (uint8_t)v;
-        }
+        for (int v = lane; v < N; v += 32) { comp[v] = (uint8_t)v; eld[v] = (uint8_t)v; }
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
             valid += __shfl_xor_sync(kFull, valid, o);
@@ -511,15 +528,117 @@ template <int W, bool PHI_GLOBAL> struct Warp {
         __syncwarp();
         sort_edges();
         __syncwarp();
-        // ---- the sweep
+        // ---- tie flags (the keys are about to be overwritten by the rank matrix)
+        for (int k0 = 0; k0 < m; k0 += 32) {
+            const int r = k0 + lane;
+            if (r + 1 < m && K[r] == K[r + 1]) P[r] |= (uint16_t)kTie;
+        }
+        __syncwarp();
+        // ---- H0: Kruskal, 32 edges checked per step
+        for (int k0 = 0; k0 < m && ncomp > 1; k0 += 32) {
+            const int r = k0 + lane;
+            const uint32_t pij = r < m ? P[r] : 0u;
+            bool cand = false;
+            if (r < m) cand = comp[(pij >> 8) & 63] != comp[pij & 255];
+            uint32_t bal = __ballot_sync(kFull, cand);
+            while (bal && ncomp > 1) {
+                const int src = __ffs(bal) - 1;
+                bal &= bal - 1;
+                const uint32_t q = __shfl_sync(kFull, pij, src);
+                const int i = (q >> 8) & 63, j = q & 255;
+                const int ci = comp[i], cj = comp[j];
+                if (ci == cj) continue;
+                const int ei = eld[ci], ej = eld[cj];
+                const float d = key_float(K[k0 + src]);
+                if (d != 0.0f) {
+                    if (lane == 0) {
+                        const size_t o = ((size_t)b * N + n0) * 2;
+                        p.bd0[o] = 0.0f;
+                        p.bd0[o + 1] = d;
+                        if (p.pr0) { p.pr0[o] = min(ei, ej); p.pr0[o + 1] = c2(i) + j; }
+                    }
+                    ++n0;
+                }
+                __syncwarp();
+                for (int v = lane; v < N; v += 32)
+                    if (comp[v] == ci) comp[v] = (uint8_t)cj;
+                if (lane == 0) { eld[cj] = (uint8_t)max(ei, ej); P[k0 + src] |= (uint16_t)kMst; }
+                __syncwarp();
+                --ncomp;
+            }
+        }
+        __syncwarp();
+        // ---- rank matrix T (0xFFFF = edge absent) over region A
+        {
+            uint32_t* T32 = reinterpret_cast<uint32_t*>(T);
+            const int words = N * ldt / 2;
+            for (int q = lane; q < words; q += 32) T32[q] = 0xFFFFFFFFu;
+            __syncwarp();
+            for (int k0 = 0; k0 < m; k0 += 32) {
+                const int r = k0 + lane;
+                if (r < m) {
+                    const uint32_t pij = P[r];
+                    const int i = (pij >> 8) & 63, j = pij & 255;
+                    T[i * ldt + j] = (uint16_t)r;
+                    T[j * ldt + i] = (uint16_t)r;
+                }
+            }
+            __syncwarp();
+        }
+        // ---- which edges can give birth to a real class: no apex at their own time
+        //      (packed u16 min over v of max(T[i][v], T[j][v]); tie-run members are always visited)
+        {
+            const int nw2 = ldt / 2;
+            for (int k0 = 0; k0 < Epad; k0 += 32) {
+                const int r = k0 + lane;
+                bool vis = false;
+                if (r < m) {
+                    const uint32_t pij = P[r];
+                    if (!(pij & kMst)) {
+                        const bool tied = (pij & kTie) || (r > 0 && (P[r - 1] & kTie));
+                        if (tied) vis = true;
+                        else {
+                            const uint32_t* Ti = reinterpret_cast<const uint32_t*>(T + ((pij >> 8) & 63) * ldt);
+                            const uint32_t* Tj = reinterpret_cast<const uint32_t*>(T + (pij & 255) * ldt);
+                            uint32_t mn = 0xFFFFFFFFu;
+                            for (int w = 0; w < nw2; ++w) mn = __vminu2(mn, __vmaxu2(Ti[w], Tj[w]));
+                            const uint32_t mm = min(mn & 0xFFFFu, mn >> 16);
+                            vis = mm > (uint32_t)r;
+                        }
+                    }
+                }
+                const uint32_t bal = __ballot_sync(kFull, vis);
+                if (lane == 0) visit[k0 >> 5] = bal;
+            }
+        }
+        // ---- PHI := 0
+        for (int q = lane; q < m * W; q += 32) phi[q] = 0;
+        __syncwarp();
+        // ---- the sweep through the live spans
         int r = 0;
         while (r < m && !overflow) {
-            const uint32_t key = K[r];
-            int r1 = r + 1;
-            while (r1 < m && K[r1] == key) ++r1;
-            if (r1 - r == 1) fast_edge(p, b, r, key);
-            else tie_run(p, b, r, r1, key);
-            r = r1;
+            if (!live_any()) {
+                // jump to the next rank where a class can be born
+                int wq = r >> 5;
+                uint32_t bits = visit[wq] & (kFull << (r & 31));
+                const int nwords = Epad >> 5;
+                while (!bits && ++wq < nwords) bits = visit[wq];
+                if (!bits) break;
+                r = 32 * wq + __ffs(bits) - 1;
+                if (r >= m) break;
+            }
+            const uint32_t pij = P[r];
+            const bool tied = (pij & kTie) || (r > 0 && (P[r - 1] & kTie));
+            if (!tied) { single_edge(r); ++r; }
+            else {
+                int r0 = r;
+                while (r0 > 0 && (P[r0 - 1] & kTie)) --r0;
+                int r1 = r;
+                while (P[r1] & kTie) ++r1;
+                ++r1;
+                tie_run(r0, r1);
+                r = r1;
+            }
         }
         if (!overflow) {
             // cycles still alive at thresh are essential
@@ -527,13 +646,14 @@ template <int W, bool PHI_GLOBAL> struct Warp {
             for (int w = 0; w < W; ++w) {
                 uint32_t bits = live[w];
                 while (bits) {
-                    int s = __ffs(bits) - 1;
+                    const int s = __ffs(bits) - 1;
                     bits &= bits - 1;
                     if (n1 < R) {
                         if (lane == 0) {
                             rec[n1] = brank[32 * w + s];
-                            rec[R + n1] = kEssential;
+                            rec[R + n1] = bkey[32 * w + s];
                             rec[2 * R + n1] = kEssential;
+                            rec[3 * R + n1] = kEssential;
                         }
                         ++n1;
                     } else overflow = true;
@@ -556,11 +676,11 @@ template <int W, bool PHI_GLOBAL> struct Warp {
             int base = n0;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                int v = lane + 32 * h;
-                bool is = v < N && eld[comp[v]] == v;
-                uint32_t bal = __ballot_sync(kFull, is);
+                const int v = lane + 32 * h;
+                const bool is = v < N && eld[comp[v]] == v;
+                const uint32_t bal = __ballot_sync(kFull, is);
                 if (is) {
-                    size_t o = ((size_t)b * N + base + __popc(bal & lanemask_lt())) * 2;
+                    const size_t o = ((size_t)b * N + base + __popc(bal & lanemask_lt())) * 2;
                     p.bd0[o] = 0.0f;
                     p.bd0[o + 1] = __int_as_float(0x7F800000);
                     if (p.pr0) { p.pr0[o] = v; p.pr0[o + 1] = -1; }
@@ -572,17 +692,17 @@ template <int W, bool PHI_GLOBAL> struct Warp {
         // ---- H1 rows in ripser's order: descending birth rank
         int st = nan_seen ? TDA_ST_NAN_INPUT : 0;
         for (int k = lane; k < n1; k += 32) {
-            uint32_t br = rec[k];
+            const uint32_t br = rec[k];
             int pos = 0;
             for (int t = 0; t < n1; ++t) pos += rec[t] > br;
             if (pos < p.cap1) {
-                size_t o = ((size_t)b * p.cap1 + pos) * 2;
-                uint32_t dk = rec[R + k], tr = rec[2 * R + k];
-                p.bd1[o] = key_float(K[br]);
+                const size_t o = ((size_t)b * p.cap1 + pos) * 2;
+                const uint32_t dk = rec[2 * R + k], tr = rec[3 * R + k];
+                p.bd1[o] = key_float(rec[R + k]);
                 p.bd1[o + 1] = (tr == kEssential) ? __int_as_float(0x7F800000) : key_float(dk);
                 if (p.pr1) {
-                    int pij = P[br];
-                    p.pr1[o] = c2(pij >> 8) + (pij & 255);
+                    const uint32_t pij = P[br];
+                    p.pr1[o] = c2((pij >> 8) & 63) + (pij & 255);
                     p.pr1[o + 1] = (tr == kEssential) ? -1ll : (long long)tr;
                 }
             }
@@ -598,7 +718,7 @@ template <int W, bool PHI_GLOBAL> struct Warp {
 };
 
 template <int W, bool PHI_GLOBAL>
-__global__ void __launch_bounds__(256) rips_small_kernel(Params p) {
+__global__ void __launch_bounds__(128) rips_small_kernel(Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef Layout<W, PHI_GLOBAL> L;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -609,25 +729,27 @@ __global__ void __launch_bounds__(256) rips_small_kernel(Params p) {
     Warp<W, PHI_GLOBAL> s;
     s.lane = lane;
     s.N = N;
+    s.ld = p.ld;
     s.E = c2(N);
     s.Epad = L::epad(N);
     s.R = L::recs(N);
-    s.adj = (unsigned long long*)base;           base += kMaxN * 8;
-    s.runadj = (unsigned long long*)base;        base += kMaxN * 8;
-    s.K = (uint32_t*)base;                       base += (size_t)s.Epad * 4;
-    s.R1 = (uint32_t*)base;                      base += L::region1(N);
-    s.hist = (uint32_t*)base;                    base += 256 * 4;
-    if (PHI_GLOBAL) {
-        s.rec = p.rec_global + (size_t)gw * 3 * s.R;
-        s.phi = p.phi_global + (size_t)gw * s.E * W;
-    } else {
-        s.rec = (uint32_t*)base;                 base += (size_t)s.R * 12;
-        s.phi = s.R1;
-    }
-    s.P = (uint16_t*)base;                       base += (size_t)s.Epad * 2;
+    s.ldt = L::ldt(N);
+    s.K = (uint32_t*)base;
+    s.hist = (uint32_t*)(base + (size_t)s.Epad * 4);
+    s.T = (uint16_t*)base;                       base += L::region_a(N);
+    s.K2 = (uint32_t*)base;
+    s.P2 = (uint16_t*)(base + (size_t)s.Epad * 4);
+    s.phi = PHI_GLOBAL ? p.phi_global + (size_t)gw * s.E * W : (uint32_t*)base;
+    base += L::region_c(N);
+    s.P = (uint16_t*)base;                       base += L::a16((size_t)s.Epad * 2);
+    if (PHI_GLOBAL) s.rec = p.rec_global + (size_t)gw * 4 * s.R;
+    else { s.rec = (uint32_t*)base;              base += (size_t)s.R * 16; }
+    s.visit = (uint32_t*)base;                   base += (size_t)s.Epad / 8;
+    s.bkey = (uint32_t*)base;                    base += 32 * W * 4;
     s.brank = (uint16_t*)base;                   base += 32 * W * 2;
     s.comp = (uint8_t*)base;                     base += kMaxN;
     s.eld = (uint8_t*)base;
+    s.defv = p.defv_global + (size_t)gw * s.Epad;
     const int total = p.worklist ? *p.n_work : p.B;
     for (int t = gw; t < total; t += nw) {
         const int b = p.worklist ? p.worklist[t] : t;
@@ -636,11 +758,12 @@ __global__ void __launch_bounds__(256) rips_small_kernel(Params p) {
     }
 }
 
-// workspace layout: [0..15] int counters ; list1[B] ; list2[B] ; phi scratch ; rec scratch
+// workspace layout: counters ; list1[B] ; list2[B] ; tie-run scratch ; phi scratch ; rec scratch
 constexpr int kLastW = 64;
-constexpr int kLastGrid = 148;  // one single-warp CTA per SM on the last tier
+constexpr int kLastGrid = 148;   // one single-warp CTA per SM on the last tier
+constexpr int kMaxWarps = 148 * 16;  // upper bound on resident warps of any tier
 struct WsLayout {
-    size_t counters, list1, list2, phi, rec, total;
+    size_t counters, list1, list2, defv, phi, rec, total;
 };
 static WsLayout ws_layout(int B, int N) {
     WsLayout w;
@@ -648,8 +771,9 @@ static WsLayout ws_layout(int B, int N) {
     w.counters = o; o += 64;
     w.list1 = o; o += ((size_t)B * 4 + 63) & ~(size_t)63;
     w.list2 = o; o += ((size_t)B * 4 + 63) & ~(size_t)63;
+    w.defv = o; o += (size_t)kMaxWarps * Layout<2, false>::epad(N);
     w.phi = o; o += (size_t)kLastGrid * c2(N) * kLastW * 4;
-    w.rec = o; o += (size_t)kLastGrid * 3 * Layout<kLastW, true>::recs(N) * 4;
+    w.rec = o; o += (size_t)kLastGrid * 4 * Layout<kLastW, true>::recs(N) * 4;
     w.total = o;
     return w;
 }
@@ -695,9 +819,11 @@ extern "C" int tda_rips_h01_batched(const float* D, int B, int N, int ld, long l
     p.thresh = thresh;
     p.bd0 = bd0; p.pr0 = pr0; p.bd1 = bd1; p.pr1 = pr1; p.counts = counts; p.status = status; p.cap1 = cap1;
     p.phi_global = nullptr; p.rec_global = nullptr;
+    p.defv_global = (uint8_t*)(w8 + wl.defv);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms > 148) sms = 148;
     // tier 1: W=2, shared-memory PHI, 4 warps per CTA, as many CTAs per SM as shared memory allows
     {
         p.worklist = nullptr; p.n_work = nullptr;
@@ -706,7 +832,7 @@ extern "C" int tda_rips_h01_batched(const float* D, int B, int N, int ld, long l
         size_t smem = Layout<2, false>::bytes(N) * wpb;
         int per_sm = (int)((227 * 1024) / (smem + 1024));
         if (per_sm < 1) per_sm = 1;
-        if (per_sm > 16) per_sm = 16;
+        if (per_sm > 4) per_sm = 4;   // 16 warps per SM at most (kMaxWarps)
         long long need = ((long long)B + wpb - 1) / wpb;
         int grid = (int)((long long)sms * per_sm < need ? (long long)sms * per_sm : need);
         e = launch_tier<2, false>(p, wpb, grid, st);
