@@ -40,8 +40,12 @@ namespace rips_small {
 constexpr int kMaxN = 64;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 constexpr uint32_t kEssential = 0xFFFFFFFFu;
-constexpr uint32_t kMst = 0x4000u;   // P flag: edge merges two components (H0 death)
-constexpr uint32_t kTie = 0x8000u;   // P flag: the next edge in the order has the same length
+// P[rank] = j | i << 6 | flags
+constexpr uint32_t kMst = 1u << 12;      // edge merges two components (H0 death)
+constexpr uint32_t kTie = 1u << 13;      // the next edge in the order has the same length
+constexpr uint32_t kTiePrev = 1u << 14;  // the previous edge in the order has the same length
+__device__ __forceinline__ int p_i(uint32_t p) { return (p >> 6) & 63; }
+__device__ __forceinline__ int p_j(uint32_t p) { return p & 63; }
 
 struct Params {
     const float* D;
@@ -81,6 +85,9 @@ template <int W, bool PHI_GLOBAL> struct Layout {
         size_t s1 = (size_t)epad(N) * 6, s2 = PHI_GLOBAL ? 0 : (size_t)c2(N) * W * 4;
         return a16(s1 > s2 ? s1 : s2);
     }
+    static __host__ __device__ size_t off_p(int N) { return region_a(N) + region_c(N); }
+    static __host__ __device__ size_t off_rec(int N) { return off_p(N) + a16((size_t)epad(N) * 2); }
+    static __host__ __device__ size_t off_visit(int N) { return off_rec(N) + (PHI_GLOBAL ? 0 : (size_t)recs(N) * 16); }
     static __host__ __device__ size_t bytes(int N) {
         size_t s = region_a(N) + region_c(N);
         s += a16((size_t)epad(N) * 2);                        // P
@@ -110,24 +117,38 @@ __device__ __forceinline__ int tri_index(int x, int y, int z) {
     return c3(a) + c2(b) + c;
 }
 
-template <int W, bool PHI_GLOBAL> struct Warp {
-    // ---- per-warp storage
-    uint32_t* K;      // region A during the sort
-    uint32_t* hist;   // region A, behind K
-    uint16_t* T;      // region A after Kruskal: rank matrix, row stride ldt
-    uint32_t* K2;     // region C during the sort
-    uint16_t* P2;
-    uint32_t* phi;    // region C afterwards (or global): PHI[rank][W]
-    uint16_t* P;      // (i << 8 | j) | flags, by rank
-    uint32_t* rec;    // [4][R]: birth rank, birth key, death key, death triangle
-    uint32_t* visit;  // bitmap over ranks: a real class may be born here
-    uint32_t* bkey;   // per slot: key of the birth edge
-    uint16_t* brank;  // per slot: rank of the birth edge
-    uint8_t* comp;
-    uint8_t* eld;
-    uint8_t* defv;    // tie runs only (global scratch): defining apex of an apparent run edge
+template <int W, bool PHI_GLOBAL, int NT> struct Warp {
+    typedef Layout<W, PHI_GLOBAL> L;
+    // ---- per-warp storage: everything is an offset from `base` (compile-time when NT > 0)
+    unsigned char* base;
+    uint32_t* phi_g;   // PHI_GLOBAL tiers
+    uint32_t* rec_g;
+    uint8_t* defv_g;   // tie runs only (global scratch): defining apex of an apparent run edge
     const float* Db;
-    int lane, N, E, Epad, R, ldt, ld;
+    int lane, Nrt, ld;
+    __device__ __forceinline__ int n() const { return NT > 0 ? NT : Nrt; }
+    __device__ __forceinline__ int e() const { return c2(n()); }
+    __device__ __forceinline__ int epad() const { return L::epad(n()); }
+    __device__ __forceinline__ int rcap() const { return L::recs(n()); }
+    __device__ __forceinline__ int ldtv() const { return L::ldt(n()); }
+    // region A: sort keys + histogram, later the rank matrix T (row stride ldtv())
+    __device__ __forceinline__ uint32_t* K() const { return (uint32_t*)base; }
+    __device__ __forceinline__ uint32_t* hist() const { return (uint32_t*)(base + (size_t)epad() * 4); }
+    __device__ __forceinline__ uint16_t* T() const { return (uint16_t*)base; }
+    // region C: sort ping-pong, later PHI[rank][W]
+    __device__ __forceinline__ uint32_t* K2() const { return (uint32_t*)(base + L::region_a(n())); }
+    __device__ __forceinline__ uint16_t* P2() const { return (uint16_t*)(base + L::region_a(n()) + (size_t)epad() * 4); }
+    __device__ __forceinline__ uint32_t* phi() const { return PHI_GLOBAL ? phi_g : (uint32_t*)(base + L::region_a(n())); }
+    // P[rank] = j | i << 6 | flags
+    __device__ __forceinline__ uint16_t* P() const { return (uint16_t*)(base + L::off_p(n())); }
+    // death records [4][R]: birth rank, birth key, death key, death triangle
+    __device__ __forceinline__ uint32_t* rec() const { return PHI_GLOBAL ? rec_g : (uint32_t*)(base + L::off_rec(n())); }
+    __device__ __forceinline__ uint32_t* visit() const { return (uint32_t*)(base + L::off_visit(n())); }
+    __device__ __forceinline__ uint32_t* bkey() const { return (uint32_t*)(base + L::off_visit(n()) + (size_t)epad() / 8); }
+    __device__ __forceinline__ uint16_t* brank() const { return (uint16_t*)(base + L::off_visit(n()) + (size_t)epad() / 8 + 32 * W * 4); }
+    __device__ __forceinline__ uint8_t* comp() const { return base + L::off_visit(n()) + (size_t)epad() / 8 + 32 * W * 6; }
+    __device__ __forceinline__ uint8_t* eld() const { return comp() + kMaxN; }
+    __device__ __forceinline__ uint8_t* defv() const { return defv_g; }
     // ---- per-window uniform state
     uint32_t live[W], used[W];
     int n0, n1, ncomp, m;
@@ -160,7 +181,7 @@ template <int W, bool PHI_GLOBAL> struct Warp {
             __syncwarp();
             for (int q = lane; q < upto; q += 32) {
 #pragma unroll
-                for (int w = 0; w < W; ++w) phi[(size_t)q * W + w] &= live[w];
+                for (int w = 0; w < W; ++w) phi()[(size_t)q * W + w] &= live[w];
             }
             __syncwarp();
             bool room = false;
@@ -178,10 +199,10 @@ template <int W, bool PHI_GLOBAL> struct Warp {
         const int s = alloc_slot(upto);
         if (s < 0) return;
         if (lane == 0) {
-            brank[s] = (uint16_t)r;
-            bkey[s] = key;
+            brank()[s] = (uint16_t)r;
+            bkey()[s] = key;
 #pragma unroll
-            for (int w = 0; w < W; ++w) phi[(size_t)r * W + w] = (w == (s >> 5)) ? (1u << (s & 31)) : 0u;
+            for (int w = 0; w < W; ++w) phi()[(size_t)r * W + w] = (w == (s >> 5)) ? (1u << (s & 31)) : 0u;
         }
         __syncwarp();
     }
@@ -212,20 +233,20 @@ template <int W, bool PHI_GLOBAL> struct Warp {
                 while (bits) {
                     const int s = __ffs(bits) - 1;
                     bits &= bits - 1;
-                    const int ag = brank[32 * w + s];
+                    const int ag = brank()[32 * w + s];
                     if (ag > age) { age = ag; slot = 32 * w + s; }
                 }
             }
             const int sw = slot >> 5;
             const uint32_t sb = 1u << (slot & 31);
-            const uint32_t bk = bkey[slot];
+            const uint32_t bk = bkey()[slot];
             if (bk != curkey) {  // non-zero persistence: keep a record
-                if (n1 < R) {
+                if (n1 < rcap()) {
                     if (lane == 0) {
-                        rec[n1] = (uint32_t)age;
-                        rec[R + n1] = bk;
-                        rec[2 * R + n1] = curkey;
-                        rec[3 * R + n1] = (uint32_t)tri_index(a, b, v);
+                        rec()[n1] = (uint32_t)age;
+                        rec()[rcap() + n1] = bk;
+                        rec()[2 * rcap() + n1] = curkey;
+                        rec()[3 * rcap() + n1] = (uint32_t)tri_index(a, b, v);
                     }
                     ++n1;
                 } else {
@@ -253,7 +274,7 @@ template <int W, bool PHI_GLOBAL> struct Warp {
             if (absorb) {
                 __syncwarp();
                 for (int q = lane; q < upto; q += 32) {
-                    uint32_t* e = phi + (size_t)q * W;
+                    uint32_t* e = phi() + (size_t)q * W;
                     if (e[sw] & sb) {
 #pragma unroll
                         for (int w = 0; w < W; ++w) e[w] ^= cv[w];
@@ -266,17 +287,17 @@ template <int W, bool PHI_GLOBAL> struct Warp {
 
     // ------------------------------------------------------------------ one single (untied) edge
     __device__ __forceinline__ void single_edge(int r) {
-        const uint32_t pij = P[r];
+        const uint32_t pij = P()[r];
         if (pij & kMst) return;  // PHI[r] stays 0: live cocycles extend by 0 over a merging edge
-        const int i = (pij >> 8) & 63, j = pij & 255;
-        const uint16_t* Ti = T + i * ldt;
-        const uint16_t* Tj = T + j * ldt;
+        const int i = p_i(pij), j = p_j(pij);
+        const uint16_t* Ti = T() + i * ldtv();
+        const uint16_t* Tj = T() + j * ldtv();
         const int v1 = lane + 32;
         uint32_t ta[2], tb[2];
         ta[0] = 0xFFFFu; tb[0] = 0xFFFFu;
         ta[1] = 0xFFFFu; tb[1] = 0xFFFFu;
-        if (lane < N) { ta[0] = Ti[lane]; tb[0] = Tj[lane]; }
-        if (v1 < N) { ta[1] = Ti[v1]; tb[1] = Tj[v1]; }
+        if (lane < n()) { ta[0] = Ti[lane]; tb[0] = Tj[lane]; }
+        if (v1 < n()) { ta[1] = Ti[v1]; tb[1] = Tj[v1]; }
         bool in[2];
         in[0] = ta[0] < (uint32_t)r && tb[0] < (uint32_t)r;
         in[1] = ta[1] < (uint32_t)r && tb[1] < (uint32_t)r;
@@ -294,8 +315,8 @@ template <int W, bool PHI_GLOBAL> struct Warp {
 #pragma unroll
             for (int w = 0; w < W; ++w) c[h][w] = 0;
             if (in[h]) {
-                const uint32_t* pa = phi + (size_t)ta[h] * W;
-                const uint32_t* pb = phi + (size_t)tb[h] * W;
+                const uint32_t* pa = phi() + (size_t)ta[h] * W;
+                const uint32_t* pb = phi() + (size_t)tb[h] * W;
 #pragma unroll
                 for (int w = 0; w < W; ++w) c[h][w] = pa[w] ^ pb[w];
             }
@@ -307,7 +328,7 @@ template <int W, bool PHI_GLOBAL> struct Warp {
             xtop[w] = __shfl_sync(kFull, (vtop >> 5) ? c[1][w] : c[0][w], vtop & 31) & live[w];
         if (lane == 0) {
 #pragma unroll
-            for (int w = 0; w < W; ++w) phi[(size_t)r * W + w] = xtop[w];
+            for (int w = 0; w < W; ++w) phi()[(size_t)r * W + w] = xtop[w];
         }
         uint32_t anyc = 0;
 #pragma unroll
@@ -331,21 +352,21 @@ template <int W, bool PHI_GLOBAL> struct Warp {
     // by apex vdef (the top of G)
     __device__ __forceinline__ void run_group(int a, int b, int rab, uint32_t G0, uint32_t G1, int vdef,
                                               int r0, int r1, uint32_t curkey) {
-        const uint16_t* Ta = T + a * ldt;
-        const uint16_t* Tb = T + b * ldt;
+        const uint16_t* Ta = T() + a * ldtv();
+        const uint16_t* Tb = T() + b * ldtv();
         uint32_t pe[W];
         if (vdef >= 0) {
-            const uint32_t* x = phi + (size_t)Ta[vdef] * W;
-            const uint32_t* y = phi + (size_t)Tb[vdef] * W;
+            const uint32_t* x = phi() + (size_t)Ta[vdef] * W;
+            const uint32_t* y = phi() + (size_t)Tb[vdef] * W;
 #pragma unroll
             for (int w = 0; w < W; ++w) pe[w] = (x[w] ^ y[w]) & live[w];
             if (lane == 0) {
 #pragma unroll
-                for (int w = 0; w < W; ++w) phi[(size_t)rab * W + w] = pe[w];
+                for (int w = 0; w < W; ++w) phi()[(size_t)rab * W + w] = pe[w];
             }
         } else {
 #pragma unroll
-            for (int w = 0; w < W; ++w) pe[w] = phi[(size_t)rab * W + w];
+            for (int w = 0; w < W; ++w) pe[w] = phi()[(size_t)rab * W + w];
         }
         uint32_t c[2][W];
         bool isdef[2] = {false, false};
@@ -359,12 +380,12 @@ template <int W, bool PHI_GLOBAL> struct Warp {
             for (int w = 0; w < W; ++w) c[h][w] = 0;
             if (in && v != vdef) {
                 const int ra = Ta[v], rb = Tb[v];
-                const uint32_t* x = phi + (size_t)ra * W;
-                const uint32_t* y = phi + (size_t)rb * W;
+                const uint32_t* x = phi() + (size_t)ra * W;
+                const uint32_t* y = phi() + (size_t)rb * W;
 #pragma unroll
                 for (int w = 0; w < W; ++w) c[h][w] = (pe[w] ^ x[w] ^ y[w]) & live[w];
-                if (ra >= r0 && defv[ra - r0] == b) { isdef[h] = true; defq[h] = ra; }
-                else if (rb >= r0 && defv[rb - r0] == a) { isdef[h] = true; defq[h] = rb; }
+                if (ra >= r0 && defv()[ra - r0] == b) { isdef[h] = true; defq[h] = ra; }
+                else if (rb >= r0 && defv()[rb - r0] == a) { isdef[h] = true; defq[h] = rb; }
                 if (!isdef[h]) {
 #pragma unroll
                     for (int w = 0; w < W; ++w) anyc |= c[h][w];
@@ -377,28 +398,28 @@ template <int W, bool PHI_GLOBAL> struct Warp {
         for (int h = 0; h < 2; ++h) {
             if (isdef[h]) {
 #pragma unroll
-                for (int w = 0; w < W; ++w) phi[(size_t)defq[h] * W + w] = c[h][w] & live[w];
+                for (int w = 0; w < W; ++w) phi()[(size_t)defq[h] * W + w] = c[h][w] & live[w];
             }
         }
         __syncwarp();
     }
 
     __device__ __forceinline__ void tie_run(int r0, int r1) {
-        const uint32_t p0 = P[r0];
-        const uint32_t curkey = float_key(dist((p0 >> 8) & 63, p0 & 255));
+        const uint32_t p0 = P()[r0];
+        const uint32_t curkey = float_key(dist(p_i(p0), p_j(p0)));
         // pass 1 (rank order): apparent pairs inside the run take no slot.  A cycle-creating run edge
         // is apparent iff its first cofacet (largest apex among the triangles present once the whole
         // run has entered) has it as youngest edge.
         for (int pr = r0; pr < r1 && !overflow; ++pr) {
-            const uint32_t pij = P[pr];
+            const uint32_t pij = P()[pr];
             uint8_t dv = 254;  // merging edge
             if (!(pij & kMst)) {
-                const int i = (pij >> 8) & 63, j = pij & 255;
-                const uint16_t* Ti = T + i * ldt;
-                const uint16_t* Tj = T + j * ldt;
+                const int i = p_i(pij), j = p_j(pij);
+                const uint16_t* Ti = T() + i * ldtv();
+                const uint16_t* Tj = T() + j * ldtv();
                 const int v1 = lane + 32;
-                const bool in0 = lane < N && Ti[lane] < r1 && Tj[lane] < r1;
-                const bool in1 = v1 < N && Ti[v1] < r1 && Tj[v1] < r1;
+                const bool in0 = lane < n() && Ti[lane] < r1 && Tj[lane] < r1;
+                const bool in1 = v1 < n() && Ti[v1] < r1 && Tj[v1] < r1;
                 const uint32_t G0 = __ballot_sync(kFull, in0), G1 = __ballot_sync(kFull, in1);
                 dv = 255;
                 if (G0 | G1) {
@@ -407,13 +428,13 @@ template <int W, bool PHI_GLOBAL> struct Warp {
                 }
                 if (dv == 255) birth(pr, r1, curkey);
             }
-            if (lane == 0) defv[pr - r0] = dv;
+            if (lane == 0) defv()[pr - r0] = dv;
         }
         __syncwarp();
         if (overflow || !live_any()) return;
         // pass 2: the run's triangles in descending index: a desc, b desc, apex c desc (c < b < a)
-        for (int a = N - 1; a >= 2; --a) {
-            const uint16_t* Ta = T + a * ldt;
+        for (int a = n() - 1; a >= 2; --a) {
+            const uint16_t* Ta = T() + a * ldtv();
             const int vb1 = lane + 32;
             const uint32_t B0 = __ballot_sync(kFull, lane < a && Ta[lane] < r1);
             const uint32_t B1 = __ballot_sync(kFull, vb1 < a && Ta[vb1] < r1);
@@ -422,7 +443,7 @@ template <int W, bool PHI_GLOBAL> struct Warp {
                 while (bits) {
                     const int bb = 32 * hb + 31 - __clz(bits);
                     bits &= ~(1u << (bb & 31));
-                    const uint16_t* Tb = T + bb * ldt;
+                    const uint16_t* Tb = T() + bb * ldtv();
                     const int rab = Ta[bb];
                     const bool ab_run = rab >= r0;
                     bool in[2];
@@ -439,7 +460,7 @@ template <int W, bool PHI_GLOBAL> struct Warp {
                     if (!(G0 | G1)) continue;
                     int vdef = -1;
                     if (ab_run) {
-                        const int dv = defv[rab - r0];
+                        const int dv = defv()[rab - r0];
                         if (dv < 254 && dv < bb) vdef = dv;
                     }
                     run_group(a, bb, rab, G0, G1, vdef, r0, r1, curkey);
@@ -449,25 +470,25 @@ template <int W, bool PHI_GLOBAL> struct Warp {
         }
     }
 
-    // ------------------------------------------------------------------ radix sort of (K, P)
+    // ------------------------------------------------------------------ radix sort of (K(), P())
     __device__ __forceinline__ void sort_edges() {
-        uint32_t* srcK = K; uint16_t* srcP = P;
-        uint32_t* dstK = K2; uint16_t* dstP = P2;
+        uint32_t* srcK = K(); uint16_t* srcP = P();
+        uint32_t* dstK = K2(); uint16_t* dstP = P2();
         const uint32_t lt = lanemask_lt();
         for (int pass = 0; pass < 4; ++pass) {
             const int shift = 8 * pass;
 #pragma unroll
-            for (int t = 0; t < 8; ++t) hist[lane + 32 * t] = 0;
+            for (int t = 0; t < 8; ++t) hist()[lane + 32 * t] = 0;
             __syncwarp();
-            for (int k0 = 0; k0 < Epad; k0 += 32) {
+            for (int k0 = 0; k0 < epad(); k0 += 32) {
                 const uint32_t dg = (srcK[k0 + lane] >> shift) & 255u;
                 const uint32_t peers = __match_any_sync(kFull, dg);
-                if ((peers & lt) == 0) hist[dg] += __popc(peers);
+                if ((peers & lt) == 0) hist()[dg] += __popc(peers);
                 __syncwarp();
             }
             uint32_t loc[8], sum = 0;
 #pragma unroll
-            for (int t = 0; t < 8; ++t) { loc[t] = hist[lane * 8 + t]; sum += loc[t]; }
+            for (int t = 0; t < 8; ++t) { loc[t] = hist()[lane * 8 + t]; sum += loc[t]; }
             uint32_t incl = sum;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -477,18 +498,18 @@ template <int W, bool PHI_GLOBAL> struct Warp {
             uint32_t run = incl - sum;
             __syncwarp();
 #pragma unroll
-            for (int t = 0; t < 8; ++t) { hist[lane * 8 + t] = run; run += loc[t]; }
+            for (int t = 0; t < 8; ++t) { hist()[lane * 8 + t] = run; run += loc[t]; }
             __syncwarp();
-            for (int k0 = 0; k0 < Epad; k0 += 32) {
+            for (int k0 = 0; k0 < epad(); k0 += 32) {
                 const uint32_t key = srcK[k0 + lane];
                 const uint16_t pay = srcP[k0 + lane];
                 const uint32_t dg = (key >> shift) & 255u;
                 const uint32_t peers = __match_any_sync(kFull, dg);
-                const uint32_t pos = hist[dg] + __popc(peers & lt);
+                const uint32_t pos = hist()[dg] + __popc(peers & lt);
                 __syncwarp();
                 dstK[pos] = key;
                 dstP[pos] = pay;
-                if ((peers & lt) == 0) hist[dg] += __popc(peers);
+                if ((peers & lt) == 0) hist()[dg] += __popc(peers);
                 __syncwarp();
             }
             uint32_t* tk = srcK; srcK = dstK; dstK = tk;
@@ -501,24 +522,24 @@ template <int W, bool PHI_GLOBAL> struct Warp {
         Db = p.D + (size_t)b * p.strideB;
         overflow = false;
         n0 = n1 = 0;
-        ncomp = N;
+        ncomp = n();
 #pragma unroll
         for (int w = 0; w < W; ++w) live[w] = used[w] = 0;
         // ---- keys, initial order = descending edge index
         int valid = 0, nan_seen = 0;
-        for (int k = E + lane; k < Epad; k += 32) { K[k] = 0xFFFFFFFFu; P[k] = 0; }
-        for (int row = 0; row < N - 1; ++row) {
-            for (int i = row + 1 + lane; i < N; i += 32) {
+        for (int k = e() + lane; k < epad(); k += 32) { K()[k] = 0xFFFFFFFFu; P()[k] = 0; }
+        for (int row = 0; row < n() - 1; ++row) {
+            for (int i = row + 1 + lane; i < n(); i += 32) {
                 const float d = __ldg(Db + (size_t)row * ld + i) + 0.0f;
                 const bool ok = d <= p.thresh;
                 nan_seen |= (d != d);
-                const int k = E - 1 - (c2(i) + row);
-                K[k] = ok ? float_key(d) : 0xFFFFFFFFu;
-                P[k] = (uint16_t)((i << 8) | row);
+                const int k = e() - 1 - (c2(i) + row);
+                K()[k] = ok ? float_key(d) : 0xFFFFFFFFu;
+                P()[k] = (uint16_t)((i << 6) | row);
                 valid += ok;
             }
         }
-        for (int v = lane; v < N; v += 32) { comp[v] = (uint8_t)v; eld[v] = (uint8_t)v; }
+        for (int v = lane; v < n(); v += 32) { comp()[v] = (uint8_t)v; eld()[v] = (uint8_t)v; }
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
             valid += __shfl_xor_sync(kFull, valid, o);
@@ -531,28 +552,34 @@ template <int W, bool PHI_GLOBAL> struct Warp {
         // ---- tie flags (the keys are about to be overwritten by the rank matrix)
         for (int k0 = 0; k0 < m; k0 += 32) {
             const int r = k0 + lane;
-            if (r + 1 < m && K[r] == K[r + 1]) P[r] |= (uint16_t)kTie;
+            if (r < m) {
+                const uint32_t kr = K()[r];
+                uint32_t f = 0;
+                if (r + 1 < m && K()[r + 1] == kr) f |= kTie;
+                if (r > 0 && K()[r - 1] == kr) f |= kTiePrev;
+                if (f) P()[r] |= (uint16_t)f;
+            }
         }
         __syncwarp();
         // ---- H0: Kruskal, 32 edges checked per step
         for (int k0 = 0; k0 < m && ncomp > 1; k0 += 32) {
             const int r = k0 + lane;
-            const uint32_t pij = r < m ? P[r] : 0u;
+            const uint32_t pij = r < m ? P()[r] : 0u;
             bool cand = false;
-            if (r < m) cand = comp[(pij >> 8) & 63] != comp[pij & 255];
+            if (r < m) cand = comp()[p_i(pij)] != comp()[p_j(pij)];
             uint32_t bal = __ballot_sync(kFull, cand);
             while (bal && ncomp > 1) {
                 const int src = __ffs(bal) - 1;
                 bal &= bal - 1;
                 const uint32_t q = __shfl_sync(kFull, pij, src);
-                const int i = (q >> 8) & 63, j = q & 255;
-                const int ci = comp[i], cj = comp[j];
+                const int i = p_i(q), j = p_j(q);
+                const int ci = comp()[i], cj = comp()[j];
                 if (ci == cj) continue;
-                const int ei = eld[ci], ej = eld[cj];
-                const float d = key_float(K[k0 + src]);
+                const int ei = eld()[ci], ej = eld()[cj];
+                const float d = key_float(K()[k0 + src]);
                 if (d != 0.0f) {
                     if (lane == 0) {
-                        const size_t o = ((size_t)b * N + n0) * 2;
+                        const size_t o = ((size_t)b * n() + n0) * 2;
                         p.bd0[o] = 0.0f;
                         p.bd0[o + 1] = d;
                         if (p.pr0) { p.pr0[o] = min(ei, ej); p.pr0[o + 1] = c2(i) + j; }
@@ -560,9 +587,9 @@ template <int W, bool PHI_GLOBAL> struct Warp {
                     ++n0;
                 }
                 __syncwarp();
-                for (int v = lane; v < N; v += 32)
-                    if (comp[v] == ci) comp[v] = (uint8_t)cj;
-                if (lane == 0) { eld[cj] = (uint8_t)max(ei, ej); P[k0 + src] |= (uint16_t)kMst; }
+                for (int v = lane; v < n(); v += 32)
+                    if (comp()[v] == ci) comp()[v] = (uint8_t)cj;
+                if (lane == 0) { eld()[cj] = (uint8_t)max(ei, ej); P()[k0 + src] |= (uint16_t)kMst; }
                 __syncwarp();
                 --ncomp;
             }
@@ -570,36 +597,36 @@ template <int W, bool PHI_GLOBAL> struct Warp {
         __syncwarp();
         // ---- rank matrix T (0xFFFF = edge absent) over region A
         {
-            uint32_t* T32 = reinterpret_cast<uint32_t*>(T);
-            const int words = N * ldt / 2;
+            uint32_t* T32 = reinterpret_cast<uint32_t*>(T());
+            const int words = n() * ldtv() / 2;
             for (int q = lane; q < words; q += 32) T32[q] = 0xFFFFFFFFu;
             __syncwarp();
             for (int k0 = 0; k0 < m; k0 += 32) {
                 const int r = k0 + lane;
                 if (r < m) {
-                    const uint32_t pij = P[r];
-                    const int i = (pij >> 8) & 63, j = pij & 255;
-                    T[i * ldt + j] = (uint16_t)r;
-                    T[j * ldt + i] = (uint16_t)r;
+                    const uint32_t pij = P()[r];
+                    const int i = p_i(pij), j = p_j(pij);
+                    T()[i * ldtv() + j] = (uint16_t)r;
+                    T()[j * ldtv() + i] = (uint16_t)r;
                 }
             }
             __syncwarp();
         }
         // ---- which edges can give birth to a real class: no apex at their own time
-        //      (packed u16 min over v of max(T[i][v], T[j][v]); tie-run members are always visited)
+        //      (packed u16 min over v of max(T()[i][v], T()[j][v]); tie-run members are always visited)
         {
-            const int nw2 = ldt / 2;
-            for (int k0 = 0; k0 < Epad; k0 += 32) {
+            const int nw2 = ldtv() / 2;
+            for (int k0 = 0; k0 < epad(); k0 += 32) {
                 const int r = k0 + lane;
                 bool vis = false;
                 if (r < m) {
-                    const uint32_t pij = P[r];
+                    const uint32_t pij = P()[r];
                     if (!(pij & kMst)) {
-                        const bool tied = (pij & kTie) || (r > 0 && (P[r - 1] & kTie));
+                        const bool tied = (pij & (kTie | kTiePrev)) != 0;
                         if (tied) vis = true;
                         else {
-                            const uint32_t* Ti = reinterpret_cast<const uint32_t*>(T + ((pij >> 8) & 63) * ldt);
-                            const uint32_t* Tj = reinterpret_cast<const uint32_t*>(T + (pij & 255) * ldt);
+                            const uint32_t* Ti = reinterpret_cast<const uint32_t*>(T() + (p_i(pij)) * ldtv());
+                            const uint32_t* Tj = reinterpret_cast<const uint32_t*>(T() + (p_j(pij)) * ldtv());
                             uint32_t mn = 0xFFFFFFFFu;
                             for (int w = 0; w < nw2; ++w) mn = __vminu2(mn, __vmaxu2(Ti[w], Tj[w]));
                             const uint32_t mm = min(mn & 0xFFFFu, mn >> 16);
@@ -608,11 +635,11 @@ template <int W, bool PHI_GLOBAL> struct Warp {
                     }
                 }
                 const uint32_t bal = __ballot_sync(kFull, vis);
-                if (lane == 0) visit[k0 >> 5] = bal;
+                if (lane == 0) visit()[k0 >> 5] = bal;
             }
         }
         // ---- PHI := 0
-        for (int q = lane; q < m * W; q += 32) phi[q] = 0;
+        for (int q = lane; q < m * W; q += 32) phi()[q] = 0;
         __syncwarp();
         // ---- the sweep through the live spans
         int r = 0;
@@ -620,21 +647,21 @@ template <int W, bool PHI_GLOBAL> struct Warp {
             if (!live_any()) {
                 // jump to the next rank where a class can be born
                 int wq = r >> 5;
-                uint32_t bits = visit[wq] & (kFull << (r & 31));
-                const int nwords = Epad >> 5;
-                while (!bits && ++wq < nwords) bits = visit[wq];
+                uint32_t bits = visit()[wq] & (kFull << (r & 31));
+                const int nwords = epad() >> 5;
+                while (!bits && ++wq < nwords) bits = visit()[wq];
                 if (!bits) break;
                 r = 32 * wq + __ffs(bits) - 1;
                 if (r >= m) break;
             }
-            const uint32_t pij = P[r];
-            const bool tied = (pij & kTie) || (r > 0 && (P[r - 1] & kTie));
+            const uint32_t pij = P()[r];
+            const bool tied = (pij & (kTie | kTiePrev)) != 0;
             if (!tied) { single_edge(r); ++r; }
             else {
                 int r0 = r;
-                while (r0 > 0 && (P[r0 - 1] & kTie)) --r0;
+                while (r0 > 0 && (P()[r0 - 1] & kTie)) --r0;
                 int r1 = r;
-                while (P[r1] & kTie) ++r1;
+                while (P()[r1] & kTie) ++r1;
                 ++r1;
                 tie_run(r0, r1);
                 r = r1;
@@ -648,12 +675,12 @@ template <int W, bool PHI_GLOBAL> struct Warp {
                 while (bits) {
                     const int s = __ffs(bits) - 1;
                     bits &= bits - 1;
-                    if (n1 < R) {
+                    if (n1 < rcap()) {
                         if (lane == 0) {
-                            rec[n1] = brank[32 * w + s];
-                            rec[R + n1] = bkey[32 * w + s];
-                            rec[2 * R + n1] = kEssential;
-                            rec[3 * R + n1] = kEssential;
+                            rec()[n1] = brank()[32 * w + s];
+                            rec()[rcap() + n1] = bkey()[32 * w + s];
+                            rec()[2 * rcap() + n1] = kEssential;
+                            rec()[3 * rcap() + n1] = kEssential;
                         }
                         ++n1;
                     } else overflow = true;
@@ -677,10 +704,10 @@ template <int W, bool PHI_GLOBAL> struct Warp {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int v = lane + 32 * h;
-                const bool is = v < N && eld[comp[v]] == v;
+                const bool is = v < n() && eld()[comp()[v]] == v;
                 const uint32_t bal = __ballot_sync(kFull, is);
                 if (is) {
-                    const size_t o = ((size_t)b * N + base + __popc(bal & lanemask_lt())) * 2;
+                    const size_t o = ((size_t)b * n() + base + __popc(bal & lanemask_lt())) * 2;
                     p.bd0[o] = 0.0f;
                     p.bd0[o + 1] = __int_as_float(0x7F800000);
                     if (p.pr0) { p.pr0[o] = v; p.pr0[o + 1] = -1; }
@@ -692,17 +719,17 @@ template <int W, bool PHI_GLOBAL> struct Warp {
         // ---- H1 rows in ripser's order: descending birth rank
         int st = nan_seen ? TDA_ST_NAN_INPUT : 0;
         for (int k = lane; k < n1; k += 32) {
-            const uint32_t br = rec[k];
+            const uint32_t br = rec()[k];
             int pos = 0;
-            for (int t = 0; t < n1; ++t) pos += rec[t] > br;
+            for (int t = 0; t < n1; ++t) pos += rec()[t] > br;
             if (pos < p.cap1) {
                 const size_t o = ((size_t)b * p.cap1 + pos) * 2;
-                const uint32_t dk = rec[2 * R + k], tr = rec[3 * R + k];
-                p.bd1[o] = key_float(rec[R + k]);
+                const uint32_t dk = rec()[2 * rcap() + k], tr = rec()[3 * rcap() + k];
+                p.bd1[o] = key_float(rec()[rcap() + k]);
                 p.bd1[o + 1] = (tr == kEssential) ? __int_as_float(0x7F800000) : key_float(dk);
                 if (p.pr1) {
-                    const uint32_t pij = P[br];
-                    p.pr1[o] = c2((pij >> 8) & 63) + (pij & 255);
+                    const uint32_t pij = P()[br];
+                    p.pr1[o] = c2(p_i(pij)) + (p_j(pij));
                     p.pr1[o + 1] = (tr == kEssential) ? -1ll : (long long)tr;
                 }
             }
@@ -717,39 +744,22 @@ template <int W, bool PHI_GLOBAL> struct Warp {
     }
 };
 
-template <int W, bool PHI_GLOBAL>
+template <int W, bool PHI_GLOBAL, int NT>
 __global__ void __launch_bounds__(128) rips_small_kernel(Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef Layout<W, PHI_GLOBAL> L;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5;
     const int gw = blockIdx.x * wpb + wib, nw = gridDim.x * wpb;
-    const int N = p.N;
-    unsigned char* base = smem_raw + (size_t)wib * L::bytes(N);
-    Warp<W, PHI_GLOBAL> s;
+    const int N = NT > 0 ? NT : p.N;
+    Warp<W, PHI_GLOBAL, NT> s;
+    s.base = smem_raw + (size_t)wib * L::bytes(N);
     s.lane = lane;
-    s.N = N;
+    s.Nrt = N;
     s.ld = p.ld;
-    s.E = c2(N);
-    s.Epad = L::epad(N);
-    s.R = L::recs(N);
-    s.ldt = L::ldt(N);
-    s.K = (uint32_t*)base;
-    s.hist = (uint32_t*)(base + (size_t)s.Epad * 4);
-    s.T = (uint16_t*)base;                       base += L::region_a(N);
-    s.K2 = (uint32_t*)base;
-    s.P2 = (uint16_t*)(base + (size_t)s.Epad * 4);
-    s.phi = PHI_GLOBAL ? p.phi_global + (size_t)gw * s.E * W : (uint32_t*)base;
-    base += L::region_c(N);
-    s.P = (uint16_t*)base;                       base += L::a16((size_t)s.Epad * 2);
-    if (PHI_GLOBAL) s.rec = p.rec_global + (size_t)gw * 4 * s.R;
-    else { s.rec = (uint32_t*)base;              base += (size_t)s.R * 16; }
-    s.visit = (uint32_t*)base;                   base += (size_t)s.Epad / 8;
-    s.bkey = (uint32_t*)base;                    base += 32 * W * 4;
-    s.brank = (uint16_t*)base;                   base += 32 * W * 2;
-    s.comp = (uint8_t*)base;                     base += kMaxN;
-    s.eld = (uint8_t*)base;
-    s.defv = p.defv_global + (size_t)gw * s.Epad;
+    s.phi_g = PHI_GLOBAL ? p.phi_global + (size_t)gw * c2(N) * W : nullptr;
+    s.rec_g = PHI_GLOBAL ? p.rec_global + (size_t)gw * 4 * L::recs(N) : nullptr;
+    s.defv_g = p.defv_global + (size_t)gw * L::epad(N);
     const int total = p.worklist ? *p.n_work : p.B;
     for (int t = gw; t < total; t += nw) {
         const int b = p.worklist ? p.worklist[t] : t;
@@ -778,14 +788,14 @@ static WsLayout ws_layout(int B, int N) {
     return w;
 }
 
-template <int W, bool G>
+template <int W, bool G, int NT>
 static cudaError_t launch_tier(const Params& p, int warps_per_block, int grid, cudaStream_t st) {
     ProfScope prof(W == 2 ? "rips_small_w2" : (W == 4 ? "rips_small_w4" : "rips_small_w64"), st);
     size_t smem = Layout<W, G>::bytes(p.N) * warps_per_block;
-    cudaError_t e = cudaFuncSetAttribute(rips_small_kernel<W, G>,
+    cudaError_t e = cudaFuncSetAttribute(rips_small_kernel<W, G, NT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    rips_small_kernel<W, G><<<grid, warps_per_block * 32, smem, st>>>(p);
+    rips_small_kernel<W, G, NT><<<grid, warps_per_block * 32, smem, st>>>(p);
     count_launch();
     return cudaGetLastError();
 }
@@ -835,14 +845,14 @@ extern "C" int tda_rips_h01_batched(const float* D, int B, int N, int ld, long l
         if (per_sm > 4) per_sm = 4;   // 16 warps per SM at most (kMaxWarps)
         long long need = ((long long)B + wpb - 1) / wpb;
         int grid = (int)((long long)sms * per_sm < need ? (long long)sms * per_sm : need);
-        e = launch_tier<2, false>(p, wpb, grid, st);
+        e = (N == 47) ? launch_tier<2, false, 47>(p, wpb, grid, st) : launch_tier<2, false, 0>(p, wpb, grid, st);
         if (e != cudaSuccess) return (int)e;
     }
     // tier 2: W=4 on the windows tier 1 gave up on
     {
         p.worklist = (const int*)(w8 + wl.list1); p.n_work = counters + 0;
         p.overflow_list = (int*)(w8 + wl.list2); p.n_overflow = counters + 1;
-        e = launch_tier<4, false>(p, 2, sms * 2, st);
+        e = launch_tier<4, false, 0>(p, 2, sms * 2, st);
         if (e != cudaSuccess) return (int)e;
     }
     // tier 3: W=64 with PHI in global scratch, handles every N<=64 input
@@ -851,7 +861,7 @@ extern "C" int tda_rips_h01_batched(const float* D, int B, int N, int ld, long l
         p.overflow_list = nullptr; p.n_overflow = nullptr;
         p.phi_global = (uint32_t*)(w8 + wl.phi);
         p.rec_global = (uint32_t*)(w8 + wl.rec);
-        e = launch_tier<kLastW, true>(p, 1, kLastGrid, st);
+        e = launch_tier<kLastW, true, 0>(p, 1, kLastGrid, st);
         if (e != cudaSuccess) return (int)e;
     }
     return 0;
