@@ -30,6 +30,7 @@
 //     the next tier, no host round-trip.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tda_b200.h"
@@ -81,19 +82,25 @@ template <int W, bool PHI_GLOBAL> struct Layout {
         size_t s1 = (size_t)epad(N) * 4 + 1024, s2 = (size_t)N * ldt(N) * 2;
         return a16(s1 > s2 ? s1 : s2);
     }
-    static __host__ __device__ size_t region_c(int N) {      // sort ping-pong | PHI
+    // sort ping-pong | PHI (phicap() ranks; all of them unless the region is made smaller)
+    static __host__ __device__ size_t region_c(int N) {
         size_t s1 = (size_t)epad(N) * 6, s2 = PHI_GLOBAL ? 0 : (size_t)c2(N) * W * 4;
         return a16(s1 > s2 ? s1 : s2);
     }
+    static __host__ __device__ int phicap(int N) {
+        if (PHI_GLOBAL) return c2(N);
+        const int cap = (int)(region_c(N) / (4 * W));
+        return cap < c2(N) ? cap : c2(N);
+    }
     static __host__ __device__ size_t off_p(int N) { return region_a(N) + region_c(N); }
     static __host__ __device__ size_t off_rec(int N) { return off_p(N) + a16((size_t)epad(N) * 2); }
-    static __host__ __device__ size_t off_visit(int N) { return off_rec(N) + (PHI_GLOBAL ? 0 : (size_t)recs(N) * 16); }
+    static __host__ __device__ size_t off_visit(int N) { return off_rec(N) + (PHI_GLOBAL ? 0 : (size_t)recs(N) * 12); }
     static __host__ __device__ size_t bytes(int N) {
         size_t s = region_a(N) + region_c(N);
         s += a16((size_t)epad(N) * 2);                        // P
-        s += PHI_GLOBAL ? 0 : (size_t)recs(N) * 16;           // death records
+        s += PHI_GLOBAL ? 0 : (size_t)recs(N) * 12;           // death records
         s += (size_t)epad(N) / 8;                             // visit bitmap
-        s += 32 * W * 4 + 32 * W * 2;                         // bkey, brank
+        s += 32 * W * 2;                                      // brank
         s += 2 * kMaxN;                                       // comp, eld
         return a16(s);
     }
@@ -131,6 +138,7 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
     __device__ __forceinline__ int epad() const { return L::epad(n()); }
     __device__ __forceinline__ int rcap() const { return L::recs(n()); }
     __device__ __forceinline__ int ldtv() const { return L::ldt(n()); }
+    __device__ __forceinline__ int phicap() const { return L::phicap(n()); }
     // region A: sort keys + histogram, later the rank matrix T (row stride ldtv())
     __device__ __forceinline__ uint32_t* K() const { return (uint32_t*)base; }
     __device__ __forceinline__ uint32_t* hist() const { return (uint32_t*)(base + (size_t)epad() * 4); }
@@ -141,12 +149,11 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
     __device__ __forceinline__ uint32_t* phi() const { return PHI_GLOBAL ? phi_g : (uint32_t*)(base + L::region_a(n())); }
     // P[rank] = j | i << 6 | flags
     __device__ __forceinline__ uint16_t* P() const { return (uint16_t*)(base + L::off_p(n())); }
-    // death records [4][R]: birth rank, birth key, death key, death triangle
+    // death records [3][R]: birth rank, death rank, death triangle
     __device__ __forceinline__ uint32_t* rec() const { return PHI_GLOBAL ? rec_g : (uint32_t*)(base + L::off_rec(n())); }
     __device__ __forceinline__ uint32_t* visit() const { return (uint32_t*)(base + L::off_visit(n())); }
-    __device__ __forceinline__ uint32_t* bkey() const { return (uint32_t*)(base + L::off_visit(n()) + (size_t)epad() / 8); }
-    __device__ __forceinline__ uint16_t* brank() const { return (uint16_t*)(base + L::off_visit(n()) + (size_t)epad() / 8 + 32 * W * 4); }
-    __device__ __forceinline__ uint8_t* comp() const { return base + L::off_visit(n()) + (size_t)epad() / 8 + 32 * W * 6; }
+    __device__ __forceinline__ uint16_t* brank() const { return (uint16_t*)(base + L::off_visit(n()) + (size_t)epad() / 8); }
+    __device__ __forceinline__ uint8_t* comp() const { return base + L::off_visit(n()) + (size_t)epad() / 8 + 32 * W * 2; }
     __device__ __forceinline__ uint8_t* eld() const { return comp() + kMaxN; }
     __device__ __forceinline__ uint8_t* defv() const { return defv_g; }
     // ---- per-window uniform state
@@ -195,12 +202,12 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
         overflow = true;
         return -1;
     }
-    __device__ __forceinline__ void birth(int r, int upto, uint32_t key) {
+    __device__ __forceinline__ void birth(int r, int upto) {
+        if (r >= phicap()) { overflow = true; return; }
         const int s = alloc_slot(upto);
         if (s < 0) return;
         if (lane == 0) {
             brank()[s] = (uint16_t)r;
-            bkey()[s] = key;
 #pragma unroll
             for (int w = 0; w < W; ++w) phi()[(size_t)r * W + w] = (w == (s >> 5)) ? (1u << (s & 31)) : 0u;
         }
@@ -210,7 +217,9 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
     // ------------------------------------------------------------------ deaths inside a group
     // c[h] = coboundary masks of the live cocycles on triangle (a, b, v = lane + 32 h); lanes with
     // isdef[h] carry the value of an apparent run edge they define (updated linearly, never a death)
-    __device__ __forceinline__ void resolve(int a, int b, uint32_t curkey, int upto, uint32_t (&c)[2][W],
+    // rcur = rank of the edge whose length is the death value; zero0 = first rank with that length
+    // (classes born at rank >= zero0 die with zero persistence and leave no record)
+    __device__ __forceinline__ void resolve(int a, int b, int rcur, int zero0, int upto, uint32_t (&c)[2][W],
                                             const bool (&isdef)[2]) {
         while (true) {
             uint32_t any0 = 0, any1 = 0;
@@ -239,14 +248,12 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
             }
             const int sw = slot >> 5;
             const uint32_t sb = 1u << (slot & 31);
-            const uint32_t bk = bkey()[slot];
-            if (bk != curkey) {  // non-zero persistence: keep a record
+            if (age < zero0) {  // non-zero persistence: keep a record
                 if (n1 < rcap()) {
                     if (lane == 0) {
                         rec()[n1] = (uint32_t)age;
-                        rec()[rcap() + n1] = bk;
-                        rec()[2 * rcap() + n1] = curkey;
-                        rec()[3 * rcap() + n1] = (uint32_t)tri_index(a, b, v);
+                        rec()[rcap() + n1] = (uint32_t)rcur;
+                        rec()[2 * rcap() + n1] = (uint32_t)tri_index(a, b, v);
                     }
                     ++n1;
                 } else {
@@ -286,28 +293,39 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
     }
 
     // ------------------------------------------------------------------ one single (untied) edge
-    __device__ __forceinline__ void single_edge(int r) {
-        const uint32_t pij = P()[r];
-        if (pij & kMst) return;  // PHI[r] stays 0: live cocycles extend by 0 over a merging edge
+    // Stage B of the sweep pipeline: everything about edge `pij` that does not depend on PHI.
+    struct Edge {
+        uint32_t pij;
+        uint32_t ta[2], tb[2];  // ranks of (i, v) and (j, v) for the apexes v = lane, lane + 32
+    };
+    __device__ __forceinline__ Edge fetch_edge(uint32_t pij) const {
+        Edge ed;
+        ed.pij = pij;
         const int i = p_i(pij), j = p_j(pij);
         const uint16_t* Ti = T() + i * ldtv();
         const uint16_t* Tj = T() + j * ldtv();
         const int v1 = lane + 32;
-        uint32_t ta[2], tb[2];
-        ta[0] = 0xFFFFu; tb[0] = 0xFFFFu;
-        ta[1] = 0xFFFFu; tb[1] = 0xFFFFu;
-        if (lane < n()) { ta[0] = Ti[lane]; tb[0] = Tj[lane]; }
-        if (v1 < n()) { ta[1] = Ti[v1]; tb[1] = Tj[v1]; }
+        ed.ta[0] = 0xFFFFu; ed.tb[0] = 0xFFFFu;
+        ed.ta[1] = 0xFFFFu; ed.tb[1] = 0xFFFFu;
+        if (lane < n()) { ed.ta[0] = Ti[lane]; ed.tb[0] = Tj[lane]; }
+        if (v1 < n()) { ed.ta[1] = Ti[v1]; ed.tb[1] = Tj[v1]; }
+        return ed;
+    }
+    // Stage C: the PHI-dependent part
+    __device__ __forceinline__ void process_edge(int r, const Edge& ed) {
+        if (ed.pij & kMst) return;  // PHI[r] stays 0: live cocycles extend by 0 over a merging edge
+        const int i = p_i(ed.pij), j = p_j(ed.pij);
         bool in[2];
-        in[0] = ta[0] < (uint32_t)r && tb[0] < (uint32_t)r;
-        in[1] = ta[1] < (uint32_t)r && tb[1] < (uint32_t)r;
+        in[0] = ed.ta[0] < (uint32_t)r && ed.tb[0] < (uint32_t)r;
+        in[1] = ed.ta[1] < (uint32_t)r && ed.tb[1] < (uint32_t)r;
         const uint32_t G0 = __ballot_sync(kFull, in[0]);
         const uint32_t G1 = __ballot_sync(kFull, in[1]);
         if (!(G0 | G1)) {  // no apex yet: a real class is born
-            birth(r, r, float_key(dist(i, j)));
+            birth(r, r);
             return;
         }
         if (!live_any()) return;
+        if (r >= phicap()) { overflow = true; return; }
         // apparent pair (e, top triangle): extend every live cocycle over e, test the other apexes
         uint32_t c[2][W];
 #pragma unroll
@@ -315,8 +333,8 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
 #pragma unroll
             for (int w = 0; w < W; ++w) c[h][w] = 0;
             if (in[h]) {
-                const uint32_t* pa = phi() + (size_t)ta[h] * W;
-                const uint32_t* pb = phi() + (size_t)tb[h] * W;
+                const uint32_t* pa = phi() + (size_t)ed.ta[h] * W;
+                const uint32_t* pb = phi() + (size_t)ed.tb[h] * W;
 #pragma unroll
                 for (int w = 0; w < W; ++w) c[h][w] = pa[w] ^ pb[w];
             }
@@ -343,7 +361,7 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
         __syncwarp();
         if (__ballot_sync(kFull, anyc != 0)) {
             const bool nodef[2] = {false, false};
-            resolve(i, j, float_key(dist(i, j)), r + 1, c, nodef);
+            resolve(i, j, r, r, r + 1, c, nodef);
         }
     }
 
@@ -351,7 +369,7 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
     // triangles (a, b, v), v < b < a, v in (G0, G1); vdef >= 0: (a,b) is an apparent run edge defined
     // by apex vdef (the top of G)
     __device__ __forceinline__ void run_group(int a, int b, int rab, uint32_t G0, uint32_t G1, int vdef,
-                                              int r0, int r1, uint32_t curkey) {
+                                              int r0, int r1) {
         const uint16_t* Ta = T() + a * ldtv();
         const uint16_t* Tb = T() + b * ldtv();
         uint32_t pe[W];
@@ -393,7 +411,7 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
             }
         }
         __syncwarp();
-        if (__ballot_sync(kFull, anyc != 0)) resolve(a, b, curkey, r1, c, isdef);
+        if (__ballot_sync(kFull, anyc != 0)) resolve(a, b, r0, r0, r1, c, isdef);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             if (isdef[h]) {
@@ -405,8 +423,11 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
     }
 
     __device__ __forceinline__ void tie_run(int r0, int r1) {
-        const uint32_t p0 = P()[r0];
-        const uint32_t curkey = float_key(dist(p_i(p0), p_j(p0)));
+        if (r1 > phicap()) {
+            // the run may touch PHI beyond this tier's capacity; only matters if a class can be alive
+            overflow = true;
+            return;
+        }
         // pass 1 (rank order): apparent pairs inside the run take no slot.  A cycle-creating run edge
         // is apparent iff its first cofacet (largest apex among the triangles present once the whole
         // run has entered) has it as youngest edge.
@@ -426,7 +447,7 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
                     const int vt = G1 ? 63 - __clz(G1) : 31 - __clz(G0);
                     if (Ti[vt] < pr && Tj[vt] < pr) dv = (uint8_t)vt;
                 }
-                if (dv == 255) birth(pr, r1, curkey);
+                if (dv == 255) birth(pr, r1);
             }
             if (lane == 0) defv()[pr - r0] = dv;
         }
@@ -463,7 +484,7 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
                         const int dv = defv()[rab - r0];
                         if (dv < 254 && dv < bb) vdef = dv;
                     }
-                    run_group(a, bb, rab, G0, G1, vdef, r0, r1, curkey);
+                    run_group(a, bb, rab, G0, G1, vdef, r0, r1);
                     if (overflow || !live_any()) return;
                 }
             }
@@ -639,32 +660,35 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
             }
         }
         // ---- PHI := 0
-        for (int q = lane; q < m * W; q += 32) phi()[q] = 0;
+        for (int q = lane; q < min(m, phicap()) * W; q += 32) phi()[q] = 0;
         __syncwarp();
         // ---- the sweep through the live spans
-        int r = 0;
-        while (r < m && !overflow) {
-            if (!live_any()) {
-                // jump to the next rank where a class can be born
-                int wq = r >> 5;
-                uint32_t bits = visit()[wq] & (kFull << (r & 31));
-                const int nwords = epad() >> 5;
-                while (!bits && ++wq < nwords) bits = visit()[wq];
-                if (!bits) break;
-                r = 32 * wq + __ffs(bits) - 1;
-                if (r >= m) break;
-            }
-            const uint32_t pij = P()[r];
-            const bool tied = (pij & (kTie | kTiePrev)) != 0;
-            if (!tied) { single_edge(r); ++r; }
-            else {
-                int r0 = r;
-                while (r0 > 0 && (P()[r0 - 1] & kTie)) --r0;
-                int r1 = r;
-                while (P()[r1] & kTie) ++r1;
-                ++r1;
-                tie_run(r0, r1);
-                r = r1;
+        {
+            int r = 0;
+            while (r < m && !overflow) {
+                if (!live_any()) {
+                    // jump to the next rank where a class can be born
+                    int wq = r >> 5;
+                    uint32_t bits = visit()[wq] & (kFull << (r & 31));
+                    const int nwords = epad() >> 5;
+                    while (!bits && ++wq < nwords) bits = visit()[wq];
+                    if (!bits) break;
+                    r = 32 * wq + __ffs(bits) - 1;
+                    if (r >= m) break;
+                }
+                const uint32_t pij = P()[r];
+                if (pij & (kTie | kTiePrev)) {
+                    int r0 = r;
+                    while (r0 > 0 && (P()[r0 - 1] & kTie)) --r0;
+                    int r1 = r;
+                    while (P()[r1] & kTie) ++r1;
+                    ++r1;
+                    tie_run(r0, r1);
+                    r = r1;
+                } else {
+                    if (!(pij & kMst)) process_edge(r, fetch_edge(pij));
+                    ++r;
+                }
             }
         }
         if (!overflow) {
@@ -678,9 +702,8 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
                     if (n1 < rcap()) {
                         if (lane == 0) {
                             rec()[n1] = brank()[32 * w + s];
-                            rec()[rcap() + n1] = bkey()[32 * w + s];
+                            rec()[rcap() + n1] = kEssential;
                             rec()[2 * rcap() + n1] = kEssential;
-                            rec()[3 * rcap() + n1] = kEssential;
                         }
                         ++n1;
                     } else overflow = true;
@@ -724,11 +747,13 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
             for (int t = 0; t < n1; ++t) pos += rec()[t] > br;
             if (pos < p.cap1) {
                 const size_t o = ((size_t)b * p.cap1 + pos) * 2;
-                const uint32_t dk = rec()[2 * rcap() + k], tr = rec()[3 * rcap() + k];
-                p.bd1[o] = key_float(rec()[rcap() + k]);
-                p.bd1[o + 1] = (tr == kEssential) ? __int_as_float(0x7F800000) : key_float(dk);
+                const uint32_t dr = rec()[rcap() + k], tr = rec()[2 * rcap() + k];
+                const uint32_t pij = P()[br];
+                p.bd1[o] = dist(p_i(pij), p_j(pij));
+                float dth = __int_as_float(0x7F800000);
+                if (tr != kEssential) { const uint32_t pd = P()[dr]; dth = dist(p_i(pd), p_j(pd)); }
+                p.bd1[o + 1] = dth;
                 if (p.pr1) {
-                    const uint32_t pij = P()[br];
                     p.pr1[o] = c2(p_i(pij)) + (p_j(pij));
                     p.pr1[o + 1] = (tr == kEssential) ? -1ll : (long long)tr;
                 }
@@ -745,7 +770,7 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
 };
 
 template <int W, bool PHI_GLOBAL, int NT>
-__global__ void __launch_bounds__(128) rips_small_kernel(Params p) {
+__global__ void __launch_bounds__(256) rips_small_kernel(Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef Layout<W, PHI_GLOBAL> L;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -758,7 +783,7 @@ __global__ void __launch_bounds__(128) rips_small_kernel(Params p) {
     s.Nrt = N;
     s.ld = p.ld;
     s.phi_g = PHI_GLOBAL ? p.phi_global + (size_t)gw * c2(N) * W : nullptr;
-    s.rec_g = PHI_GLOBAL ? p.rec_global + (size_t)gw * 4 * L::recs(N) : nullptr;
+    s.rec_g = PHI_GLOBAL ? p.rec_global + (size_t)gw * 3 * L::recs(N) : nullptr;
     s.defv_g = p.defv_global + (size_t)gw * L::epad(N);
     const int total = p.worklist ? *p.n_work : p.B;
     for (int t = gw; t < total; t += nw) {
@@ -838,11 +863,18 @@ extern "C" int tda_rips_h01_batched(const float* D, int B, int N, int ld, long l
     {
         p.worklist = nullptr; p.n_work = nullptr;
         p.overflow_list = (int*)(w8 + wl.list1); p.n_overflow = counters + 0;
-        const int wpb = 4;
+        // two CTAs per SM, each with as many warps as shared memory allows (<= 8: kMaxWarps)
+        int wpb = (int)(((227 * 1024) / 2 - 1024) / Layout<2, false>::bytes(N));
+        if (wpb < 1) wpb = 1;
+        if (wpb > 8) wpb = 8;
+        int max_per_sm = 2;
+        if (const char* ev = getenv("TDA_RIPS_WPB")) { int v = atoi(ev); if (v >= 1 && v <= 8) wpb = v; }   // tuning knobs
+        if (const char* ev = getenv("TDA_RIPS_CTAS")) { int v = atoi(ev); if (v >= 1 && v <= 16) max_per_sm = v; }
         size_t smem = Layout<2, false>::bytes(N) * wpb;
         int per_sm = (int)((227 * 1024) / (smem + 1024));
         if (per_sm < 1) per_sm = 1;
-        if (per_sm > 4) per_sm = 4;   // 16 warps per SM at most (kMaxWarps)
+        if (per_sm > max_per_sm) per_sm = max_per_sm;
+        if (per_sm * wpb > 16) per_sm = 16 / wpb;
         long long need = ((long long)B + wpb - 1) / wpb;
         int grid = (int)((long long)sms * per_sm < need ? (long long)sms * per_sm : need);
         e = (N == 47) ? launch_tier<2, false, 47>(p, wpb, grid, st) : launch_tier<2, false, 0>(p, wpb, grid, st);
