@@ -86,6 +86,19 @@ int tda_rips_h01_medium(const float* D, const int* npts, int B, int N, int ld, l
                         float thresh, float* bd0, long long* pr0, int cap0, float* bd1, long long* pr1,
                         int cap1, int* counts, int* status, void* ws, size_t ws_bytes, void* stream);
 
+/* Rips H0+H1 for big clouds, 2 <= N <= 2048 (the 1,000-2,000 point Takens clouds of the scaling
+ * stress, BASELINE.json configs[4]; also any batch above the 64-point engine).  Same arguments,
+ * outputs and conventions as tda_rips_h01_medium.  Grid-wide cooperative phases over a chunk of
+ * clouds (edge keys, one device-wide radix sort, rank matrices, Kruskal, first-cofacet /
+ * apparent-pair classification of every edge) followed by one CTA per cloud for the serial part
+ * (cocycle sweep over the edges a live class can see).  The chunk size follows from `ws_bytes`;
+ * tda_rips_h01_large_workspace_bytes returns a size that holds min(B, what fits 12 GB) clouds.
+ * Replaces ripser(...) inside compute_audio_persistence, /root/reference/scripts/utils.py:131. */
+size_t tda_rips_h01_large_workspace_bytes(int B, int N);
+int tda_rips_h01_large(const float* D, const int* npts, int B, int N, int ld, long long strideB,
+                       float thresh, float* bd0, long long* pr0, int cap0, float* bd1, long long* pr1,
+                       int cap1, int* counts, int* status, void* ws, size_t ws_bytes, void* stream);
+
 /* Same contract with HOST pointers: chunks the batch, overlaps H2D / kernels / D2H on internal
  * streams, returns when all outputs are in host memory.  `device` is the CUDA ordinal. */
 int tda_rips_h01_host(const float* D, int B, int N, float thresh, float* bd0, long long* pr0,

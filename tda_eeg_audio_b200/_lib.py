@@ -36,6 +36,8 @@ SIGNATURES = {
     "tda_eeg_features_host": (_i, [_vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "tda_rips_h01_medium_workspace_bytes": (_sz, [_i, _i]),
     "tda_rips_h01_medium": (_i, [_vp, _vp, _i, _i, _i, _ll, _f, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "tda_rips_h01_large_workspace_bytes": (_sz, [_i, _i]),
+    "tda_rips_h01_large": (_i, [_vp, _vp, _i, _i, _i, _ll, _f, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "tda_rips_h01_host": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i]),
 }
 

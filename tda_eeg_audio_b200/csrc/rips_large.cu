@@ -1,0 +1,1016 @@
+// rips_large.cu — Vietoris–Rips H0+H1 (Z/2) for batches of big clouds (N <= 2048): the
+// scaling-stress Takens clouds of 1,000-2,000 points (BASELINE.json configs[4]) and, because the
+// algorithm does far less serial work than the CTA-per-cloud sweep of rips_medium.cu, any batch
+// of clouds above the 64-point engine.
+//
+// Replaces ripser.ripser(point_cloud / dm, maxdim=1, thresh) as called by
+//   /root/reference/scripts/utils.py:123-132 (compute_audio_persistence)
+//
+// Not a port of Ripser.  Ripser walks the 2M columns of a 2,000-point cloud one after the other
+// (coboundary enumeration + apparent/emergent pair test per column, heap reduction for the rest).
+// Here (oracle/pcoh_large_model.cpp is the executable statement of the algorithm, validated on
+// CPU) the work is split into grid-wide data-parallel phases over ALL clouds of a chunk and a
+// short serial sweep per cloud:
+//   K1 keys      one 64-bit key per edge: cloud | order-preserving image of the f32 length | ~index
+//                (so ONE device-wide radix sort (CUB) orders every cloud by (length asc, index desc),
+//                Ripser's tie-break)
+//   K2 scatter   sorted position r -> P[r] = (i, j, tie flag), rank matrix T[i][j] = r
+//   K3 kruskal   one CTA per cloud: MST flags + the H0 pairs (elder rule for the vertex)
+//   K4 classify  one warp per edge, cooperative over the whole grid: the first cofacet of every
+//                non-MST edge (largest apex v with T[i][v], T[j][v] inside the edge's tie run or
+//                before it).  If that triangle has the edge as its youngest edge the two form an
+//                apparent zero-persistence pair (defv = v) — >99 % of all columns end here —
+//                otherwise the edge gives BIRTH to an H1 class.
+//   K5 sweep     one CTA per cloud, persistent cohomology by cocycle annotation restricted to the
+//                edges a live cocycle can see: S[v] = OR of the cocycle masks over the edges at v;
+//                an edge with (S[i] | S[j]) & live == 0 has PHI = 0 and coboundary 0 on all of
+//                its triangles and is skipped by a block-wide scan of 1,024 ranks per step.  The
+//                visited tie runs (a single edge is a run of one) are handled exactly:
+//                  A. rank order: births take a slot, visible apparent edges get
+//                     PHI[e] := PHI[i,defv] ^ PHI[j,defv]   (non-zero values live in a compact
+//                     store addressed through Q[i][j], a u16 matrix read by rows like T)
+//                  B. death loop, thread = apex: among the triangles (e, z), T[i][z], T[j][z] <
+//                     rank(e), of the visited edges the one with the LARGEST index and non-zero
+//                     coboundary mask kills its youngest class; the other classes of the mask
+//                     absorb it (PHI ^= mask wherever the dying bit is set); repeat.
+//   Capacity tiers: 256 simultaneous classes (W = 8 words; 512 above 1,024 points), then 1,024
+//   (W = 32) through a device-side hand-over list.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+#include "tda_b200.h"
+
+namespace tda {
+namespace rips_large {
+
+constexpr int kMaxN = 2048;
+constexpr uint32_t kInf = 0xFFFFFFFFu;
+constexpr uint32_t kFull = 0xFFFFFFFFu;
+constexpr uint32_t kEssential = 0xFFFFFFFFu;
+// P[r] = j | i << 11 | flags
+constexpr uint32_t kMst = 1u << 22;      // merging edge (H0 death)
+constexpr uint32_t kTieNext = 1u << 23;  // the next edge in the order has the same length
+constexpr uint32_t kBirth = 1u << 24;    // gives birth to an H1 class
+constexpr int kCapPMax = 65534;          // compact PHI entries per cloud (Q is u16, 0 = none)
+constexpr int kCapRMax = 65536;          // death records per cloud
+
+__host__ __device__ inline long long c2(long long i) { return i * (i - 1) / 2; }
+__host__ __device__ inline long long c3(long long i) { return i * (i - 1) * (i - 2) / 6; }
+__device__ __forceinline__ int p_i(uint32_t p) { return (p >> 11) & 2047; }
+__device__ __forceinline__ int p_j(uint32_t p) { return p & 2047; }
+__device__ __forceinline__ uint32_t float_key(float d) {
+    uint32_t u = __float_as_uint(d);
+    return (u >> 31) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ uint32_t tri_index(int x, int y, int z) {
+    const int a = max(x, max(y, z)), c = min(x, min(y, z)), b = x + y + z - a - c;
+    return (uint32_t)(c3(a) + c2(b) + c);
+}
+
+struct Params {
+    const float* D;
+    const int* npts;
+    long long strideB;
+    int ld, N, B;
+    float thresh;
+    float* bd0;
+    long long* pr0;
+    float* bd1;
+    long long* pr1;
+    int* counts;
+    int* status;
+    int cap0, cap1;
+    // chunk of clouds [c0, c0 + C)
+    int c0, C;
+    int ldT, ib;
+    long long Emax;
+    uint64_t* keysA;
+    uint64_t* keysB;
+    uint32_t* P;      // [C][Emax]
+    uint32_t* T;      // [C][N][ldT]
+    uint16_t* Q;      // [C][N][ldT]
+    uint16_t* defv;   // [C][Emax]
+    int* m;           // [C] number of edges <= thresh
+    int* nanflag;     // [C]
+    // per-CTA sweep scratch
+    int capP, capR;   // compact PHI entries / death records per cloud
+    uint32_t* phic;   // [grid][capP][W]
+    uint32_t* pcr;    // [grid][capP] rank of the edge of a compact entry
+    uint32_t* act;    // [grid][Emax]
+    uint32_t* rec;    // [grid][3][capR]
+    uint32_t* sglob;  // [grid][N][W] (tiers that keep S in global memory)
+    const int* worklist;
+    const int* n_work;
+    int* overflow_list;
+    int* n_overflow;
+};
+
+__device__ __forceinline__ int cloud_n(const Params& p, int b) {
+    int n = p.npts ? p.npts[b] : p.N;
+    return n < 0 ? 0 : (n > p.N ? p.N : n);
+}
+
+// ------------------------------------------------------------------------------------ K1 keys
+// thread per matrix element (row j, column i > j), coalesced along i; padding entries filled too
+__global__ void keys_kernel(Params p) {
+    const int c = blockIdx.y;
+    const int b = p.c0 + c;
+    const int n = cloud_n(p, b);
+    const long long E = c2(n);
+    const uint64_t cbits = (uint64_t)c << (32 + p.ib);
+    const uint64_t imask = (1ull << p.ib) - 1ull;
+    uint64_t* out = p.keysA + (size_t)c * p.Emax;
+    const float* Db = p.D + (size_t)b * p.strideB;
+    int nan_seen = 0;
+    const long long total = (long long)n * n;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(q / n), i = (int)(q - (long long)j * n);
+        if (i <= j) continue;
+        const float d = Db[(size_t)j * p.ld + i] + 0.0f;
+        nan_seen |= (d != d);
+        const uint32_t k32 = (d <= p.thresh) ? float_key(d) : kInf;
+        const uint64_t idx = (uint64_t)(c2(i) + j);
+        const long long pos = (long long)j * n - (long long)j * (j + 1) / 2 + (i - j - 1);
+        out[pos] = cbits | ((uint64_t)k32 << p.ib) | (~idx & imask);
+    }
+    for (long long q = E + (long long)blockIdx.x * blockDim.x + threadIdx.x; q < p.Emax; q += (long long)gridDim.x * blockDim.x)
+        out[q] = cbits | ((uint64_t)kInf << p.ib) | imask;
+    if (nan_seen) atomicOr(p.nanflag + c, 1);
+}
+
+// ------------------------------------------------------------------------------------ K2 scatter
+__global__ void scatter_kernel(Params p) {
+    const int c = blockIdx.y;
+    const uint64_t* in = p.keysB + (size_t)c * p.Emax;
+    const uint64_t imask = (1ull << p.ib) - 1ull;
+    uint32_t* Pc = p.P + (size_t)c * p.Emax;
+    uint32_t* Tc = p.T + (size_t)c * p.N * p.ldT;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < p.Emax; r += (long long)gridDim.x * blockDim.x) {
+        const uint64_t key = in[r];
+        const uint32_t k32 = (uint32_t)(key >> p.ib);
+        if (k32 == kInf) {
+            if (r == 0) p.m[c] = 0;
+            continue;
+        }
+        uint32_t nk = kInf;
+        if (r + 1 < p.Emax) nk = (uint32_t)(in[r + 1] >> p.ib);
+        if (nk == kInf) p.m[c] = (int)(r + 1);
+        const long long idx = (long long)(~key & imask);
+        long long i = (long long)((1.0 + sqrt(1.0 + 8.0 * (double)idx)) * 0.5);
+        while (c2(i) > idx) --i;
+        while (c2(i + 1) <= idx) ++i;
+        const int j = (int)(idx - c2(i));
+        Pc[r] = (uint32_t)j | ((uint32_t)i << 11) | (nk == k32 ? kTieNext : 0u);
+        Tc[(size_t)i * p.ldT + j] = (uint32_t)r;
+        Tc[(size_t)j * p.ldT + i] = (uint32_t)r;
+    }
+}
+
+// block-wide minimum of an int (every thread gets the result); sm[] holds >= 33 ints
+template <int NTH> __device__ __forceinline__ int block_min(int v, int* sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = __reduce_min_sync(kFull, v);
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    int x = lane < NTH / 32 ? sm[lane] : 0x7FFFFFFF;
+    x = __reduce_min_sync(kFull, x);
+    __syncthreads();
+    return x;
+}
+template <int NTH> __device__ __forceinline__ uint32_t block_max_u32(uint32_t v, uint32_t* sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = __reduce_max_sync(kFull, v);
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    uint32_t x = lane < NTH / 32 ? sm[lane] : 0u;
+    x = __reduce_max_sync(kFull, x);
+    __syncthreads();
+    return x;
+}
+
+// ------------------------------------------------------------------------------------ K3 kruskal
+template <int NTH> __global__ void __launch_bounds__(NTH) kruskal_kernel(Params p) {
+    __shared__ uint16_t comp[kMaxN];
+    __shared__ uint16_t eld[kMaxN];
+    __shared__ int red[34];
+    __shared__ uint32_t pub;
+    const int tid = threadIdx.x;
+    for (int c = blockIdx.x; c < p.C; c += gridDim.x) {
+        const int b = p.c0 + c;
+        const int n = cloud_n(p, b);
+        const int m = n >= 2 ? p.m[c] : 0;
+        uint32_t* Pc = p.P + (size_t)c * p.Emax;
+        const float* Db = p.D + (size_t)b * p.strideB;
+        for (int v = tid; v < n; v += NTH) { comp[v] = (uint16_t)v; eld[v] = (uint16_t)v; }
+        __syncthreads();
+        int ncomp = n, n0 = 0;
+        for (int r = 0; r < m && ncomp > 1; r += NTH) {
+            const int rr = r + tid;
+            uint32_t pe = 0;
+            bool cand = false;
+            if (rr < m) {
+                pe = Pc[rr];
+                cand = comp[p_i(pe)] != comp[p_j(pe)];
+            }
+            while (ncomp > 1) {
+                const int first = block_min<NTH>(cand ? rr : 0x7FFFFFFF, red);
+                if (first == 0x7FFFFFFF) break;
+                if (rr == first) { pub = pe; Pc[rr] = pe | kMst; cand = false; }
+                __syncthreads();
+                const uint32_t q = pub;
+                const int i = p_i(q), j = p_j(q);
+                const int ci = comp[i], cj = comp[j];
+                const int ei = eld[ci], ej = eld[cj];
+                const float d = Db[(size_t)j * p.ld + i] + 0.0f;
+                if (d != 0.0f) {
+                    if (tid == 0 && n0 < p.cap0) {
+                        const size_t o = ((size_t)b * p.cap0 + n0) * 2;
+                        p.bd0[o] = 0.0f;
+                        p.bd0[o + 1] = d;
+                        if (p.pr0) { p.pr0[o] = min(ei, ej); p.pr0[o + 1] = c2(i) + j; }
+                    }
+                    ++n0;
+                }
+                __syncthreads();
+                for (int v = tid; v < n; v += NTH)
+                    if (comp[v] == ci) comp[v] = (uint16_t)cj;
+                if (tid == 0) eld[cj] = (uint16_t)max(ei, ej);
+                __syncthreads();
+                --ncomp;
+                if (cand) cand = comp[p_i(pe)] != comp[p_j(pe)];
+            }
+        }
+        // essential classes: eldest vertex of every surviving component, ascending
+        for (int v0 = 0; v0 < n; v0 += NTH) {
+            const int v = v0 + tid;
+            const bool is = v < n && eld[comp[v]] == v;
+            const uint32_t bal = __ballot_sync(kFull, is);
+            if ((tid & 31) == 0) red[tid >> 5] = __popc(bal);
+            __syncthreads();
+            int base = n0, tot = 0;
+            for (int w = 0; w < NTH / 32; ++w) { if (w < (tid >> 5)) base += red[w]; tot += red[w]; }
+            if (is) {
+                const int pos = base + __popc(bal & ((1u << (tid & 31)) - 1u));
+                if (pos < p.cap0) {
+                    const size_t o = ((size_t)b * p.cap0 + pos) * 2;
+                    p.bd0[o] = 0.0f;
+                    p.bd0[o + 1] = __int_as_float(0x7F800000);
+                    if (p.pr0) { p.pr0[o] = v; p.pr0[o + 1] = -1; }
+                }
+            }
+            n0 += tot;
+            __syncthreads();
+        }
+        if (tid == 0) p.counts[2 * b] = n0;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------ K4 classify
+// one warp per block of 32 consecutive ranks; the non-MST ones are classified one after the other
+__global__ void __launch_bounds__(256) classify_kernel(Params p) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long blocks_per_cloud = (p.Emax + 31) / 32;
+    for (long long w = gw; w < blocks_per_cloud * p.C; w += nwarp) {
+        const int c = (int)(w / blocks_per_cloud);
+        const int rb = (int)(w - (long long)c * blocks_per_cloud) * 32;
+        const int m = p.m[c];
+        if (rb >= m) continue;
+        const int n = cloud_n(p, p.c0 + c);
+        uint32_t* Pc = p.P + (size_t)c * p.Emax;
+        const uint32_t* Tc = p.T + (size_t)c * p.N * p.ldT;
+        const uint64_t* keys = p.keysB + (size_t)c * p.Emax;
+        const int rr = rb + lane;
+        const uint32_t pe = rr < m ? Pc[rr] : kMst;
+        const uint32_t pprev = (rr > 0 && rr < m) ? Pc[rr - 1] : 0u;
+        uint32_t todo = __ballot_sync(kFull, !(pe & kMst));
+        const int top0 = (n - 1) & ~31;
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t q = __shfl_sync(kFull, pe, src);
+            const uint32_t qprev = __shfl_sync(kFull, pprev, src);
+            const int r = rb + src;
+            const int i = p_i(q), j = p_j(q);
+            const bool tied = (q & kTieNext) || (qprev & kTieNext);
+            const uint32_t k32r = tied ? (uint32_t)(keys[r] >> p.ib) : 0u;
+            const uint32_t* Ti = Tc + (size_t)i * p.ldT;
+            const uint32_t* Tj = Tc + (size_t)j * p.ldT;
+            int dv = -1;
+            for (int v0 = top0; v0 >= 0; v0 -= 32) {
+                const int v = v0 + lane;
+                uint32_t ta = kInf, tb = kInf;
+                if (v < n) { ta = Ti[v]; tb = Tj[v]; }
+                bool ina = ta < (uint32_t)r, inb = tb < (uint32_t)r;
+                const bool strict = ina && inb;
+                if (tied) {
+                    if (!ina && ta != kInf && ta > (uint32_t)r) ina = (uint32_t)(keys[ta] >> p.ib) == k32r;
+                    if (!inb && tb != kInf && tb > (uint32_t)r) inb = (uint32_t)(keys[tb] >> p.ib) == k32r;
+                }
+                const uint32_t bal = __ballot_sync(kFull, ina && inb);
+                if (bal) {
+                    const int sl = 31 - __clz(bal);
+                    const bool yes = __shfl_sync(kFull, strict, sl);
+                    dv = yes ? v0 + sl : -1;
+                    break;
+                }
+            }
+            if (lane == 0) {
+                if (dv < 0) Pc[r] = q | kBirth;
+                else p.defv[(size_t)c * p.Emax + r] = (uint16_t)dv;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ K5 sweep
+template <int NTH, int APT, int W, bool SG> struct Sweep {
+    // shared state
+    uint32_t* S;      // [n][W]  (shared or global)
+    uint32_t* hot;    // [kMaxN / 32]
+    uint32_t* live;   // [W]
+    uint32_t* used;   // [W]
+    uint32_t* brank;  // [32 W]
+    uint32_t* cv;     // [W] broadcast of the firing mask
+    uint32_t* peval;  // [W] value of the edge handled by the fast path
+    uint32_t* pub;    // [4] published edge words
+    uint32_t* red;    // [34]
+    int* ctl;         // [8]: npc, na, n1, overflow, resume, winner rank, fast-path code
+    // per-CTA global scratch
+    uint32_t* phic;
+    uint32_t* pcr;
+    uint32_t* act;
+    uint32_t* rec;
+    // per-cloud
+    const uint32_t* P;
+    const uint32_t* T;
+    uint16_t* Q;
+    const uint16_t* defv;
+    const float* Db;
+    int n, m, ldT, ld, tid, lane, warp, capP, capR;
+
+    __device__ __forceinline__ float dist(int a, int b) const {
+        return Db[(size_t)min(a, b) * ld + max(a, b)] + 0.0f;
+    }
+    __device__ __forceinline__ bool hotbit(int v) const { return (hot[v >> 5] >> (v & 31)) & 1u; }
+    __device__ __forceinline__ bool live_any() const {
+        uint32_t a = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) a |= live[w];
+        return a != 0;
+    }
+    __device__ void rebuild_hot() {
+        for (int v0 = 0; v0 < ((n + 31) & ~31); v0 += NTH) {
+            const int v = v0 + tid;
+            bool h = false;
+            if (v < n) {
+                uint32_t a = 0;
+#pragma unroll
+                for (int w = 0; w < W; ++w) a |= S[(size_t)v * W + w] & live[w];
+                h = a != 0;
+            }
+            const uint32_t bal = __ballot_sync(kFull, h);
+            if (lane == 0 && v < ((n + 31) & ~31)) hot[v >> 5] = bal;
+        }
+    }
+    // warp 0 only: append a compact PHI entry for edge (x, y) of rank pr; val = this lane's word
+    __device__ __forceinline__ bool append(int pr, int x, int y, uint32_t val) {
+        const int idx = ctl[0];
+        if (idx >= capP) { ctl[3] = 1; return false; }
+        if (lane < W) {
+            phic[(size_t)idx * W + lane] = val;
+            S[(size_t)x * W + lane] |= val;
+            S[(size_t)y * W + lane] |= val;
+        }
+        if (lane == 0) {
+            pcr[idx] = (uint32_t)pr;
+            Q[(size_t)x * ldT + y] = (uint16_t)(idx + 1);
+            Q[(size_t)y * ldT + x] = (uint16_t)(idx + 1);
+            hot[x >> 5] |= 1u << (x & 31);
+            hot[y >> 5] |= 1u << (y & 31);
+            ctl[0] = idx + 1;
+        }
+        __syncwarp();
+        return true;
+    }
+    // warp 0 only: birth / definition of one edge.  0 = no live cocycle sees it, 1 = visited,
+    // 2 = birth without a free slot (nothing changed; the CTA scrubs and calls again).
+    // Leaves the edge's value in peval[].
+    __device__ int edge_a(int pr, uint32_t pe, int dv) {
+        const int x = p_i(pe), y = p_j(pe);
+        uint32_t val = 0;
+        if (pe & kBirth) {
+            const uint32_t f = lane < W ? ~used[lane] : 0u;
+            const uint32_t bal = __ballot_sync(kFull, f != 0);
+            if (!bal) return 2;
+            const int sw = __ffs(bal) - 1;
+            const uint32_t fw = __shfl_sync(kFull, f, sw);
+            const int sb = __ffs(fw) - 1;
+            val = (lane == sw) ? (1u << sb) : 0u;
+            if (lane == sw) { used[lane] |= 1u << sb; live[lane] |= 1u << sb; }
+            if (lane == 0) brank[32 * sw + sb] = (uint32_t)pr;
+            __syncwarp();
+        } else {
+            const uint32_t t = lane < W ? (S[(size_t)x * W + lane] | S[(size_t)y * W + lane]) & live[lane] : 0u;
+            if (!__ballot_sync(kFull, t != 0)) return 0;
+            const int qa = Q[(size_t)x * ldT + dv], qb = Q[(size_t)y * ldT + dv];
+            if (lane < W) {
+                if (qa) val ^= phic[(size_t)(qa - 1) * W + lane];
+                if (qb) val ^= phic[(size_t)(qb - 1) * W + lane];
+                val &= live[lane];
+            }
+        }
+        if (lane < W) peval[lane] = val;
+        if (__ballot_sync(kFull, val != 0)) {
+            if (!append(pr, x, y, val)) return 0;
+        }
+        if (lane == 0) { act[ctl[1]] = (uint32_t)pr; ctl[1] = ctl[1] + 1; }
+        __syncwarp();
+        return 1;
+    }
+    // warp 0 only.  Returns the rank to resume from after a scrub, or r1 when done.
+    __device__ int step_a(int ra, int r1) {
+        for (int pr = ra; pr < r1; ++pr) {
+            const uint32_t pe = __ldg(P + pr);
+            if (pe & kMst) continue;
+            const int dv = (pe & kBirth) ? 0 : (int)defv[pr];
+            const int code = edge_a(pr, pe, dv);
+            if (code == 2) return pr;
+            if (ctl[3]) return r1;
+        }
+        return r1;
+    }
+    __device__ void scrub() {
+        const int npc = ctl[0];
+        for (int q = tid; q < npc * W; q += NTH) phic[q] &= live[q % W];
+        for (int q = tid; q < n * W; q += NTH) S[q] &= live[q % W];
+        __syncthreads();
+        if (tid < W) used[tid] = live[tid];
+        __syncthreads();
+    }
+    // coboundary mask of the live cocycles on triangle (x, y, z), given the value pe[] on (x, y)
+    __device__ __forceinline__ bool cob(const uint32_t (&pe)[W], int x, int y, int z, uint32_t (&c)[W]) const {
+        const int qa = Q[(size_t)x * ldT + z], qb = Q[(size_t)y * ldT + z];
+        uint32_t any = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            uint32_t v = pe[w];
+            if (qa) v ^= phic[(size_t)(qa - 1) * W + w];
+            if (qb) v ^= phic[(size_t)(qb - 1) * W + w];
+            v &= live[w];
+            c[w] = v;
+            any |= v;
+        }
+        return any != 0;
+    }
+    __device__ void load_pe(int x, int y, uint32_t (&pe)[W]) const {
+        const int q = Q[(size_t)x * ldT + y];
+#pragma unroll
+        for (int w = 0; w < W; ++w) pe[w] = q ? phic[(size_t)(q - 1) * W + w] : 0u;
+    }
+    // death loop over the visited edges act[0 .. na)
+    __device__ void step_b(int r0, int r1) {
+        const int na = ctl[1];
+        while (true) {
+            uint32_t best = 0;
+            int best_a = -1, best_z = -1;
+            for (int a = 0; a < na; ++a) {
+                const int pr = (int)act[a];
+                const uint32_t pq = __ldg(P + pr);
+                const int x = p_i(pq), y = p_j(pq);
+                uint32_t pe[W];
+                load_pe(x, y, pe);
+                const uint32_t* Tx = T + (size_t)x * ldT;
+                const uint32_t* Ty = T + (size_t)y * ldT;
+#pragma unroll
+                for (int h = APT - 1; h >= 0; --h) {
+                    const int z = tid + h * NTH;
+                    if (z < n && __ldg(Tx + z) < (uint32_t)pr && __ldg(Ty + z) < (uint32_t)pr) {
+                        uint32_t c[W];
+                        if (cob(pe, x, y, z, c)) {
+                            const uint32_t t = tri_index(x, y, z) + 1u;
+                            if (t > best) { best = t; best_a = a; best_z = z; }
+                        }
+                    }
+                }
+            }
+            const uint32_t top = block_max_u32<NTH>(best, red);
+            if (top == 0) return;
+            if (best == top) {
+                const int pr = (int)act[best_a];
+                const uint32_t pq = __ldg(P + pr);
+                uint32_t pe[W], c[W];
+                load_pe(p_i(pq), p_j(pq), pe);
+                cob(pe, p_i(pq), p_j(pq), best_z, c);
+#pragma unroll
+                for (int w = 0; w < W; ++w) cv[w] = c[w];
+                ctl[5] = pr;
+            }
+            __syncthreads();
+            // youngest class of the mask dies
+            int slot = -1, age = -1;
+            bool others = false;
+            for (int w = 0; w < W; ++w) {
+                uint32_t bits = cv[w];
+                while (bits) {
+                    const int s = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const int ag = (int)brank[32 * w + s];
+                    if (slot >= 0) others = true;
+                    if (ag > age) { age = ag; slot = 32 * w + s; }
+                }
+            }
+            const int sw = slot >> 5;
+            const uint32_t sb = 1u << (slot & 31);
+            __syncthreads();
+            if (tid == 0) {
+                if (age < r0) {  // non-zero persistence
+                    const int k = ctl[2];
+                    if (k < capR) {
+                        rec[k] = (uint32_t)age;
+                        rec[capR + k] = (uint32_t)ctl[5];
+                        rec[2 * capR + k] = top - 1u;
+                    } else ctl[3] = 1;
+                    ctl[2] = k + 1;
+                }
+                live[sw] &= ~sb;
+            }
+            if (others) {
+                const int npc = ctl[0];
+                for (int q = tid; q < npc; q += NTH) {
+                    uint32_t* e = phic + (size_t)q * W;
+                    if (e[sw] & sb) {
+                        const uint32_t pq = __ldg(P + pcr[q]);
+                        const int x = p_i(pq), y = p_j(pq);
+#pragma unroll
+                        for (int w = 0; w < W; ++w) {
+                            const uint32_t v = cv[w];
+                            if (v) {
+                                e[w] ^= v;
+                                atomicOr(S + (size_t)x * W + w, v);
+                                atomicOr(S + (size_t)y * W + w, v);
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            rebuild_hot();
+            __syncthreads();
+            if (ctl[3]) return;
+        }
+    }
+
+    // a tie run [r0, r1): A (births / definitions in rank order, warp 0, scrubs when slots run out), B
+    __device__ void generic_run(int r0, int r1) {
+        if (tid == 0) ctl[1] = 0;
+        __syncthreads();
+        int ra = r0;
+        while (true) {
+            if (warp == 0) {
+                const int nxt = step_a(ra, r1);
+                if (lane == 0) ctl[4] = nxt;
+            }
+            __syncthreads();
+            ra = ctl[4];
+            if (ra >= r1 || ctl[3]) break;
+            scrub();  // slots exhausted at rank ra: recycle the dead ones
+            bool room = false;
+            for (int w = 0; w < W; ++w) room |= (~used[w]) != 0;
+            if (!room) { if (tid == 0) ctl[3] = 1; __syncthreads(); break; }
+        }
+        if (ctl[3]) return;
+        if (ctl[1] > 0) step_b(r0, r1);
+    }
+    // an untied edge: the apex rows are fetched while warp 0 does step A, one pass decides whether
+    // anything dies (almost never), only then the general death loop runs
+    __device__ void fast_single(int pr, uint32_t pe, int dv) {
+        const int x = p_i(pe), y = p_j(pe);
+        const uint32_t* Tx = T + (size_t)x * ldT;
+        const uint32_t* Ty = T + (size_t)y * ldT;
+        const uint16_t* Qx = Q + (size_t)x * ldT;
+        const uint16_t* Qy = Q + (size_t)y * ldT;
+        uint32_t ta[APT], tb[APT];
+        int qa[APT], qb[APT];
+#pragma unroll
+        for (int h = 0; h < APT; ++h) {
+            const int z = tid + h * NTH;
+            ta[h] = kInf; tb[h] = kInf; qa[h] = 0; qb[h] = 0;
+            if (z < n) { ta[h] = __ldg(Tx + z); tb[h] = __ldg(Ty + z); qa[h] = Qx[z]; qb[h] = Qy[z]; }
+        }
+        if (warp == 0) {
+            if (lane == 0) ctl[1] = 0;
+            __syncwarp();
+            const int code = edge_a(pr, pe, dv);
+            if (lane == 0) ctl[6] = code;
+        }
+        __syncthreads();
+        const int code = ctl[6];
+        if (code == 0 || ctl[3]) return;
+        if (code == 2) { generic_run(pr, pr + 1); return; }
+        uint32_t best = 0;
+#pragma unroll
+        for (int h = 0; h < APT; ++h) {
+            if (ta[h] < (uint32_t)pr && tb[h] < (uint32_t)pr) {
+                uint32_t any = 0;
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    uint32_t v = peval[w];
+                    if (qa[h]) v ^= phic[(size_t)(qa[h] - 1) * W + w];
+                    if (qb[h]) v ^= phic[(size_t)(qb[h] - 1) * W + w];
+                    any |= v & live[w];
+                }
+                if (any) best = max(best, tri_index(x, y, tid + h * NTH) + 1u);
+            }
+        }
+        const uint32_t top = block_max_u32<NTH>(best, red);
+        if (top == 0) return;
+        step_b(pr, pr + 1);
+    }
+
+    __device__ void run(const Params& p, int c, bool rezero_q) {
+        const int b = p.c0 + c;
+        n = cloud_n(p, b);
+        m = n >= 2 ? p.m[c] : 0;
+        ldT = p.ldT;
+        ld = p.ld;
+        P = p.P + (size_t)c * p.Emax;
+        T = p.T + (size_t)c * p.N * p.ldT;
+        Q = p.Q + (size_t)c * p.N * p.ldT;
+        defv = p.defv + (size_t)c * p.Emax;
+        Db = p.D + (size_t)b * p.strideB;
+        if (n < 2) {
+            if (tid == 0) {
+                if (n == 1 && p.cap0 > 0) {
+                    const size_t o = (size_t)b * p.cap0 * 2;
+                    p.bd0[o] = 0.0f;
+                    p.bd0[o + 1] = __int_as_float(0x7F800000);
+                    if (p.pr0) { p.pr0[o] = 0; p.pr0[o + 1] = -1; }
+                }
+                p.counts[2 * b] = n;
+                p.counts[2 * b + 1] = 0;
+                p.status[b] = 0;
+            }
+            return;
+        }
+        if (rezero_q) {
+            for (size_t q = tid; q < (size_t)n * ldT; q += NTH) Q[q] = 0;
+        }
+        for (int q = tid; q < n * W; q += NTH) S[q] = 0;
+        for (int q = tid; q < kMaxN / 32; q += NTH) hot[q] = 0;
+        if (tid < W) { live[tid] = 0; used[tid] = 0; }
+        if (tid < 8) ctl[tid] = 0;
+        __syncthreads();
+        int rbase = 0;
+        while (rbase < m && !ctl[3]) {
+            // ---- this thread's edge of the chunk stays in registers while the chunk is scanned
+            const int rr = rbase + tid;
+            uint32_t pe = kMst;
+            int dv = 0;
+            if (rr < m) {
+                pe = __ldg(P + rr);
+                if (!(pe & (kMst | kBirth))) dv = defv[rr];
+            }
+            const int rend = min(rbase + NTH, m);
+            int done = rbase;
+            while (true) {
+                // first edge of the chunk a live cocycle can see (or a birth)
+                const bool flag = rr >= done && !(pe & kMst) &&
+                                  ((pe & kBirth) || hotbit(p_i(pe)) || hotbit(p_j(pe)));
+                const int first = block_min<NTH>(flag ? rr : 0x7FFFFFFF, (int*)red);
+                if (first == 0x7FFFFFFF) break;
+                if (rr == first) { pub[0] = pe; pub[2] = (uint32_t)dv; }
+                if (rr == first - 1) pub[1] = pe;
+                __syncthreads();
+                const uint32_t fpe = pub[0];
+                uint32_t ppe = 0;
+                if (first > rbase) ppe = pub[1];
+                else if (first > 0) ppe = __ldg(P + first - 1);
+                int r1 = first + 1;
+                if (!((fpe | ppe) & kTieNext)) {
+                    fast_single(first, fpe, (int)pub[2]);
+                } else {
+                    int r0 = first;
+                    while (r0 > 0 && (__ldg(P + r0 - 1) & kTieNext)) --r0;
+                    while (__ldg(P + r1 - 1) & kTieNext) ++r1;
+                    generic_run(r0, r1);
+                }
+                __syncthreads();
+                done = r1;
+                if (done >= rend || ctl[3]) break;
+            }
+            rbase = max(rbase + NTH, done);
+        }
+        __syncthreads();
+        const bool overflow = ctl[3] != 0;
+        if (overflow) {
+            if (p.overflow_list) {
+                if (tid == 0) p.overflow_list[atomicAdd(p.n_overflow, 1)] = c;
+            } else if (tid == 0) {
+                p.status[b] = TDA_ST_INTERNAL | (p.nanflag[c] ? TDA_ST_NAN_INPUT : 0);
+                p.counts[2 * b + 1] = 0;
+            }
+            __syncthreads();
+            return;
+        }
+        // ---- classes still alive are essential
+        if (tid == 0) {
+            int k = ctl[2];
+            for (int w = 0; w < W; ++w) {
+                uint32_t bits = live[w];
+                while (bits) {
+                    const int s = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    if (k < capR) {
+                        rec[k] = brank[32 * w + s];
+                        rec[capR + k] = kEssential;
+                        rec[2 * capR + k] = kEssential;
+                    }
+                    ++k;
+                }
+            }
+            ctl[2] = k;
+        }
+        __syncthreads();
+        const int n1 = ctl[2];
+        if (n1 > capR) {
+            if (tid == 0) {
+                p.status[b] = TDA_ST_INTERNAL | (p.nanflag[c] ? TDA_ST_NAN_INPUT : 0);
+                p.counts[2 * b + 1] = 0;
+            }
+            __syncthreads();
+            return;
+        }
+        // ---- H1 rows in ripser's order: descending birth rank
+        for (int k = tid; k < n1; k += NTH) {
+            const uint32_t br = rec[k];
+            int pos = 0;
+            for (int t = 0; t < n1; ++t) pos += rec[t] > br;
+            if (pos < p.cap1) {
+                const size_t o = ((size_t)b * p.cap1 + pos) * 2;
+                const uint32_t dr = rec[capR + k], tr = rec[2 * capR + k];
+                const uint32_t pb = __ldg(P + br);
+                p.bd1[o] = dist(p_i(pb), p_j(pb));
+                float dth = __int_as_float(0x7F800000);
+                if (tr != kEssential) { const uint32_t pd = __ldg(P + dr); dth = dist(p_i(pd), p_j(pd)); }
+                p.bd1[o + 1] = dth;
+                if (p.pr1) {
+                    p.pr1[o] = c2(p_i(pb)) + p_j(pb);
+                    p.pr1[o + 1] = (tr == kEssential) ? -1ll : (long long)tr;
+                }
+            }
+        }
+        if (tid == 0) {
+            p.counts[2 * b + 1] = n1;
+            p.status[b] = (p.nanflag[c] ? TDA_ST_NAN_INPUT : 0) | (n1 > p.cap1 ? TDA_ST_H1_TRUNCATED : 0);
+        }
+        __syncthreads();
+    }
+};
+
+template <int NTH, int APT, int W, bool SG>
+__global__ void __launch_bounds__(NTH) sweep_kernel(Params p, int rezero_q) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Sweep<NTH, APT, W, SG> s;
+    uint32_t* base = (uint32_t*)smem_raw;
+    s.hot = base;            base += kMaxN / 32;
+    s.live = base;           base += W;
+    s.used = base;           base += W;
+    s.brank = base;          base += 32 * W;
+    s.cv = base;             base += W;
+    s.peval = base;          base += W;
+    s.pub = base;            base += 4;
+    s.red = base;            base += 34;
+    s.ctl = (int*)base;      base += 8;
+    s.S = SG ? p.sglob + (size_t)blockIdx.x * p.N * W : base;
+    s.capP = p.capP;
+    s.capR = p.capR;
+    s.phic = p.phic + (size_t)blockIdx.x * p.capP * W;
+    s.pcr = p.pcr + (size_t)blockIdx.x * p.capP;
+    s.act = p.act + (size_t)blockIdx.x * p.Emax;
+    s.rec = p.rec + (size_t)blockIdx.x * 3 * p.capR;
+    s.tid = threadIdx.x;
+    s.lane = threadIdx.x & 31;
+    s.warp = threadIdx.x >> 5;
+    const int total = p.worklist ? *p.n_work : p.C;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int c = p.worklist ? p.worklist[t] : t;
+        s.run(p, c, rezero_q != 0);
+        __syncthreads();
+    }
+}
+
+template <int W> static size_t sweep_smem(int N, bool sg) {
+    size_t words = kMaxN / 32 + W + W + 32 * W + W + W + 4 + 34 + 8;
+    if (!sg) words += (size_t)N * W;
+    return words * 4;
+}
+
+// ------------------------------------------------------------------------------------ host side
+struct Plan {
+    int N, ldT, ib, C, grid1, grid2, nth, apt, capP, capR;
+    long long Emax;
+    size_t cub_bytes;
+    size_t keysA, keysB, P, T, Q, defv, m, nanflag, counters, list, cub, phic1, phic2, pcr, act, rec, sglob, total;
+};
+static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+static int bits_for(long long v) { int b = 1; while ((1ll << b) < v) ++b; return b; }
+constexpr int kGrid2 = 148;
+constexpr int kSms = 148;  // B200; grids and the workspace layout are sized for it
+
+// resident sweep CTAs per SM on the first tier (threads and shared memory)
+static int tier1_ctas_per_sm(int N, int nth) {
+    int by_threads = 2048 / nth;
+    int by_smem = (int)((227 * 1024) / ((N > 1024 ? sweep_smem<16>(N, false) : sweep_smem<8>(N, false)) + 1024));
+    int r = by_threads < by_smem ? by_threads : by_smem;
+    return r < 1 ? 1 : r;
+}
+
+static bool make_plan(int B, int N, size_t ws_bytes, Plan& pl) {
+    pl.N = N;
+    pl.ldT = (N + 31) & ~31;
+    pl.Emax = c2(N);
+    pl.ib = bits_for(pl.Emax);
+    pl.nth = N <= 128 ? 128 : (N <= 256 ? 256 : 1024);
+    pl.apt = N <= 1024 ? 1 : 2;
+    long long cp = 64ll * N;
+    pl.capP = (int)(cp < kCapPMax ? cp : kCapPMax);
+    pl.capR = (int)(pl.Emax < kCapRMax ? (pl.Emax < 64 ? 64 : pl.Emax) : kCapRMax);
+    const int cmax_bits = 32 - pl.ib;
+    long long cmax = 1ll << (cmax_bits > 15 ? 15 : cmax_bits);   // also the gridDim.y limit
+    const long long cap_items = (1ll << 31) - 1;
+    if (cmax * pl.Emax > cap_items) cmax = cap_items / pl.Emax;
+    if (cmax < 1) cmax = 1;
+    const int per_sm = tier1_ctas_per_sm(N, pl.nth);
+    auto layout = [&](int C) {
+        size_t o = 0;
+        pl.C = C;
+        pl.grid1 = C < kSms * per_sm ? C : kSms * per_sm;
+        pl.grid2 = C < kGrid2 ? C : kGrid2;
+        pl.counters = o; o += 256;
+        pl.m = o; o += al((size_t)C * 4);
+        pl.nanflag = o; o += al((size_t)C * 4);
+        pl.list = o; o += al((size_t)C * 4);
+        pl.keysA = o; o += al((size_t)C * pl.Emax * 8);
+        pl.keysB = o; o += al((size_t)C * pl.Emax * 8);
+        pl.P = o; o += al((size_t)C * pl.Emax * 4);
+        pl.defv = o; o += al((size_t)C * pl.Emax * 2);
+        pl.T = o; o += al((size_t)C * N * pl.ldT * 4);
+        pl.Q = o; o += al((size_t)C * N * pl.ldT * 2);
+        pl.cub_bytes = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, pl.cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+                                       (long long)C * pl.Emax, 0, 64);
+        pl.cub = o; o += al(pl.cub_bytes);
+        pl.phic1 = o; o += al((size_t)pl.grid1 * pl.capP * (N > 1024 ? 16 : 8) * 4);
+        pl.phic2 = o; o += al((size_t)pl.grid2 * pl.capP * 32 * 4);
+        pl.pcr = o; o += al((size_t)pl.grid1 * pl.capP * 4);
+        pl.act = o; o += al((size_t)pl.grid1 * pl.Emax * 4);
+        pl.rec = o; o += al((size_t)pl.grid1 * 3 * pl.capR * 4);
+        pl.sglob = o; o += al((size_t)pl.grid2 * N * 32 * 4);
+        pl.total = o;
+    };
+    long long C = B < cmax ? B : cmax;
+    if (C < 1) C = 1;
+    // sizing query (ws_bytes == 0): aim at <= 12 GB, at least one cloud
+    const size_t budget = ws_bytes ? ws_bytes : ((size_t)12 << 30);
+    layout((int)C);
+    while (pl.total > budget && C > 1) { C = (C + 1) / 2; layout((int)C); }
+    return ws_bytes == 0 || pl.total <= ws_bytes;
+}
+
+template <int NTH, int APT, int W1>
+static cudaError_t launch_sweeps(Params p, const Plan& pl, char* w8, cudaStream_t st) {
+    int* counters = (int*)(w8 + pl.counters);
+    cudaError_t e;
+    {
+        ProfScope prof("rips_large_sweep_t1", st);
+        p.worklist = nullptr; p.n_work = nullptr;
+        p.overflow_list = (int*)(w8 + pl.list); p.n_overflow = counters;
+        p.phic = (uint32_t*)(w8 + pl.phic1);
+        const size_t smem = sweep_smem<W1>(p.N, false);
+        e = cudaFuncSetAttribute(sweep_kernel<NTH, APT, W1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        const int grid = p.C < pl.grid1 ? p.C : pl.grid1;
+        sweep_kernel<NTH, APT, W1, false><<<grid, NTH, smem, st>>>(p, 0);
+        count_launch();
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    {
+        ProfScope prof("rips_large_sweep_t2", st);
+        p.worklist = (const int*)(w8 + pl.list); p.n_work = counters;
+        p.overflow_list = nullptr; p.n_overflow = nullptr;
+        p.phic = (uint32_t*)(w8 + pl.phic2);
+        constexpr bool SG = (APT > 1);
+        const size_t smem = sweep_smem<32>(p.N, SG);
+        e = cudaFuncSetAttribute(sweep_kernel<NTH, APT, 32, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        const int grid = p.C < pl.grid2 ? p.C : pl.grid2;
+        sweep_kernel<NTH, APT, 32, SG><<<grid, NTH, smem, st>>>(p, 1);
+        count_launch();
+        e = cudaGetLastError();
+    }
+    return e;
+}
+
+}  // namespace rips_large
+}  // namespace tda
+
+using namespace tda;
+using namespace tda::rips_large;
+
+extern "C" size_t tda_rips_h01_large_workspace_bytes(int B, int N) {
+    if (B < 0 || N < 2 || N > kMaxN) return 0;
+    Plan pl;
+    make_plan(B < 1 ? 1 : B, N, 0, pl);
+    return pl.total;
+}
+
+extern "C" int tda_rips_h01_large(const float* D, const int* npts, int B, int N, int ld, long long strideB,
+                                  float thresh, float* bd0, long long* pr0, int cap0, float* bd1, long long* pr1,
+                                  int cap1, int* counts, int* status, void* ws, size_t ws_bytes, void* stream) {
+    if (!D || !bd0 || !bd1 || !counts || !status || !ws || B < 0 || cap0 < 0 || cap1 < 0 || ld < N) return TDA_E_ARG;
+    if (N < 2 || N > kMaxN) return TDA_E_SIZE;
+    if (B == 0) return 0;
+    Plan pl;
+    if (ws_bytes < 1024 || !make_plan(B, N, ws_bytes, pl)) return TDA_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* w8 = (char*)ws;
+    Params p;
+    p.D = D; p.npts = npts; p.strideB = strideB ? strideB : (long long)ld * ld; p.ld = ld; p.N = N; p.B = B;
+    p.thresh = thresh;
+    p.bd0 = bd0; p.pr0 = pr0; p.bd1 = bd1; p.pr1 = pr1; p.counts = counts; p.status = status;
+    p.cap0 = cap0; p.cap1 = cap1;
+    p.ldT = pl.ldT; p.ib = pl.ib; p.Emax = pl.Emax;
+    p.keysA = (uint64_t*)(w8 + pl.keysA); p.keysB = (uint64_t*)(w8 + pl.keysB);
+    p.P = (uint32_t*)(w8 + pl.P); p.T = (uint32_t*)(w8 + pl.T); p.Q = (uint16_t*)(w8 + pl.Q);
+    p.defv = (uint16_t*)(w8 + pl.defv); p.m = (int*)(w8 + pl.m); p.nanflag = (int*)(w8 + pl.nanflag);
+    p.capP = pl.capP; p.capR = pl.capR;
+    p.phic = nullptr; p.pcr = (uint32_t*)(w8 + pl.pcr); p.act = (uint32_t*)(w8 + pl.act);
+    p.rec = (uint32_t*)(w8 + pl.rec); p.sglob = (uint32_t*)(w8 + pl.sglob);
+    p.worklist = nullptr; p.n_work = nullptr; p.overflow_list = nullptr; p.n_overflow = nullptr;
+    cudaError_t e;
+    for (int c0 = 0; c0 < B; c0 += pl.C) {
+        const int C = (B - c0) < pl.C ? (B - c0) : pl.C;
+        p.c0 = c0; p.C = C;
+        if ((e = cudaMemsetAsync(w8 + pl.counters, 0, 256, st)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemsetAsync(p.m, 0, (size_t)C * 4, st)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemsetAsync(p.nanflag, 0, (size_t)C * 4, st)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemsetAsync(p.T, 0xFF, (size_t)C * N * pl.ldT * 4, st)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemsetAsync(p.Q, 0, (size_t)C * N * pl.ldT * 2, st)) != cudaSuccess) return (int)e;
+        {
+            ProfScope prof("rips_large_keys", st);
+            long long per = ((long long)N * N + 255) / 256;
+            dim3 grid((unsigned)(per < 1024 ? per : 1024), (unsigned)C);
+            keys_kernel<<<grid, 256, 0, st>>>(p);
+            count_launch();
+            if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+        }
+        {
+            ProfScope prof("rips_large_sort", st);
+            size_t tb = pl.cub_bytes;
+            int cb = bits_for(C);
+            int end_bit = 32 + pl.ib + cb;
+            if (end_bit > 64) end_bit = 64;
+            e = cub::DeviceRadixSort::SortKeys((void*)(w8 + pl.cub), tb, (const uint64_t*)p.keysA, p.keysB,
+                                               (long long)C * pl.Emax, 0, end_bit, st);
+            count_launch(4);
+            if (e != cudaSuccess) return (int)e;
+        }
+        {
+            ProfScope prof("rips_large_scatter", st);
+            long long per = (pl.Emax + 255) / 256;
+            dim3 grid((unsigned)(per < 1024 ? per : 1024), (unsigned)C);
+            scatter_kernel<<<grid, 256, 0, st>>>(p);
+            count_launch();
+            if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+        }
+        {
+            ProfScope prof("rips_large_kruskal", st);
+            if (N <= 256) kruskal_kernel<256><<<C, 256, 0, st>>>(p);
+            else kruskal_kernel<1024><<<C, 1024, 0, st>>>(p);
+            count_launch();
+            if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+        }
+        {
+            ProfScope prof("rips_large_classify", st);
+            long long warps = ((pl.Emax + 31) / 32) * C;
+            long long blocks = (warps + 7) / 8;
+            if (blocks > 148 * 64) blocks = 148 * 64;
+            classify_kernel<<<(unsigned)blocks, 256, 0, st>>>(p);
+            count_launch();
+            if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+        }
+        if (N <= 128) e = launch_sweeps<128, 1, 8>(p, pl, w8, st);
+        else if (N <= 256) e = launch_sweeps<256, 1, 8>(p, pl, w8, st);
+        else if (N <= 1024) e = launch_sweeps<1024, 1, 8>(p, pl, w8, st);
+        else e = launch_sweeps<1024, 2, 16>(p, pl, w8, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
+}

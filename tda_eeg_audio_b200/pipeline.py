@@ -83,7 +83,7 @@ def audio_diagrams_from_envelope(env, fs=250, bands=None, window_sec=1.0, overla
     nmax = int(npts.max().item()) if npts.numel() else 0
     nmax = max(nmax, 2)
     D = takens.pairwise_distance_f32(pts[:, :nmax].contiguous(), npts, ld=nmax)
-    rips = rips_h01_batched(D, thresh=thresh, cap1=cap1, want_pairs=want_pairs, npts=npts, engine="medium")
+    rips = rips_h01_batched(D, thresh=thresh, cap1=cap1, want_pairs=want_pairs, npts=npts, engine="auto")
     return {"rips": rips, "tau": tau.view(R, nb), "idx": idx, "npts": npts, "shape": (R, nb, n_sel), "D": D}
 
 

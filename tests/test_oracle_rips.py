@@ -76,3 +76,29 @@ def test_invariants():
 def test_errors():
     with pytest.raises(Exception, match="not square"):
         rips.ripser(np.zeros((3, 4)), distance_matrix=True)
+
+
+def test_large_engine_model_matches_oracle():
+    """oracle/pcoh_large_model.cpp (the algorithm of rips_large.cu: edge classification + cocycle
+    sweep over visible edges, unified exact handling of tie runs) against the Ripser restatement."""
+    from oracle import pcoh_large
+    rng = np.random.default_rng(11)
+    for trial in range(600):
+        n = int(rng.integers(3, 26))
+        kind = trial % 5
+        if kind == 0:
+            D = inputs.sym_uniform(rng, 1, n)[0]
+        elif kind == 1:
+            D = np.round(inputs.sym_uniform(rng, 1, n)[0] * 8) / 8
+        elif kind == 2:
+            P = rng.random((n, 2)); D = np.sqrt(((P[:, None] - P[None]) ** 2).sum(-1))
+        elif kind == 3:
+            P = rng.integers(0, 4, (n, 2)).astype(float); D = np.sqrt(((P[:, None] - P[None]) ** 2).sum(-1))
+        else:
+            D = np.full((n, n), 0.5); np.fill_diagonal(D, 0)
+        thr = (np.inf, 0.6, 2.0)[trial % 3]
+        _same(rips.ripser(D.astype(np.float32), thresh=thr, distance_matrix=True), pcoh_large.rips_h01(D, thr))
+    for D in inputs.circle_cloud(rng, 2, 150):
+        a = pcoh_large.rips_h01(D, 2.0)
+        _same(rips.ripser(D, thresh=2.0, distance_matrix=True), a)
+        assert a["stats"]["visited_edges"] < a["stats"]["edges"]
