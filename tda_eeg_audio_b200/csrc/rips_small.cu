@@ -174,15 +174,22 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
     // ------------------------------------------------------------------ slots
     __device__ __forceinline__ int alloc_slot(int upto) {
         for (int attempt = 0; attempt < 2; ++attempt) {
+            // (no indexed writes inside branches: a dynamic index would push live/used, and with
+            // them the whole per-warp state, into local memory)
+            int slot = -1;
 #pragma unroll
             for (int w = 0; w < W; ++w) {
-                uint32_t f = ~used[w];
-                if (f) {
-                    int s = __ffs(f) - 1;
-                    used[w] |= 1u << s;
-                    live[w] |= 1u << s;
-                    return 32 * w + s;
+                const uint32_t f = ~used[w];
+                if (slot < 0 && f) slot = 32 * w + __ffs(f) - 1;
+            }
+            if (slot >= 0) {
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    const uint32_t bit = (w == (slot >> 5)) ? (1u << (slot & 31)) : 0u;
+                    used[w] |= bit;
+                    live[w] |= bit;
                 }
+                return slot;
             }
             // every slot has been used once: scrub the dead bits out of PHI and recycle
             __syncwarp();
@@ -770,7 +777,7 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
 };
 
 template <int W, bool PHI_GLOBAL, int NT>
-__global__ void __launch_bounds__(256) rips_small_kernel(Params p) {
+__global__ void __launch_bounds__(256, 1) rips_small_kernel(Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef Layout<W, PHI_GLOBAL> L;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
