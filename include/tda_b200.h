@@ -126,6 +126,26 @@ int tda_pers_features(const float* bd, int cap, const int* counts, int count_str
 int tda_aggregate_windows(const double* feats, int R, int Bd, int Wn, double* table, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Audio front end (FP64).
+ * tda_resample_poly_f64 replaces sig_proc.resample_poly(audio, fs_target, fs_audio) in resample_audio,
+ *   /root/reference/scripts/utils.py:77-79.  Computes y = upfirdn(h_padded, x, up, down)[n_pre_remove :
+ *   n_pre_remove + n_out] for every row, zero padding at both ends (scipy's padtype='constant').
+ *   x (n_seq, n_in) rows of stride x_stride; up <= 8 and down coprime (scipy reduces them by their
+ *   gcd); hpoly (up, qmax) DEVICE, hpoly[p][q] = h_padded[p + q*up] with zeros beyond the filter —
+ *   the Kaiser FIR scipy designs with firwin, a host-side constant like the Butterworth
+ *   coefficients; y (n_seq, n_out) rows of stride y_stride.  n_seq <= 65535 per call.
+ * tda_hilbert_envelope_f64 replaces np.abs(sig_proc.hilbert(s)) in compute_envelope,
+ *   /root/reference/scripts/utils.py:58-59 (the butter(4)+filtfilt that follows is tda_filtfilt_f64, form 1).
+ *   cuFFT Z2Z plans are cached per (device, T, n_seq) for the life of the library.
+ *   ws: tda_hilbert_envelope_workspace_bytes(n_seq, T) bytes. */
+int tda_resample_poly_f64(const double* x, long long n_seq, long long n_in, long long x_stride, int up, int down,
+                          const double* hpoly, int qmax, long long n_pre_remove, long long n_out, double* y,
+                          long long y_stride, void* stream);
+size_t tda_hilbert_envelope_workspace_bytes(long long n_seq, long long T);
+int tda_hilbert_envelope_f64(const double* x, long long n_seq, long long T, long long x_stride, double* env,
+                             long long env_stride, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Zero-phase IIR filtering of many sequences at once, FP64, scipy's exact recursion
  * (odd extension by padlen, zi scaled by the first sample, forward pass, reverse, second pass).
  * Replaces: signal.sosfiltfilt(sos, x)  /root/reference/notebooks/1_preprocesamiento.ipynb:262-263  (form 0)

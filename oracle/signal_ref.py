@@ -140,3 +140,18 @@ def eeg_distances(x, fs=250, window_size=1.0, overlap=0.75, bands=FREQ_BANDS):
         wins, _ = create_sliding_windows(y, window_size, overlap, fs)
         out.append(np.stack([correlation_to_distance(compute_correlation_matrix(w)) for w in wins]))
     return np.stack(out)
+
+
+def resample_audio(audio, fs_audio=44100, fs_target=250):
+    """/root/reference/scripts/utils.py:77-79"""
+    return signal.resample_poly(audio, fs_target, fs_audio)
+
+
+def compute_envelope(s, fs):
+    """/root/reference/scripts/utils.py:56-63"""
+    analytic = signal.hilbert(s)
+    env = np.abs(analytic)
+    nyq = fs / 2
+    cutoff = min(50, nyq * 0.9)
+    b, a = signal.butter(4, cutoff / nyq, btype="low")
+    return signal.filtfilt(b, a, env)

@@ -38,6 +38,9 @@ SIGNATURES = {
     "tda_rips_h01_medium": (_i, [_vp, _vp, _i, _i, _i, _ll, _f, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "tda_rips_h01_large_workspace_bytes": (_sz, [_i, _i]),
     "tda_rips_h01_large": (_i, [_vp, _vp, _i, _i, _i, _ll, _f, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "tda_resample_poly_f64": (_i, [_vp, _ll, _ll, _ll, _i, _i, _vp, _i, _ll, _ll, _vp, _ll, _vp]),
+    "tda_hilbert_envelope_workspace_bytes": (_sz, [_ll, _ll]),
+    "tda_hilbert_envelope_f64": (_i, [_vp, _ll, _ll, _ll, _vp, _ll, _vp, _sz, _vp]),
     "tda_rips_h01_host": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i]),
 }
 

@@ -67,3 +67,24 @@ def signal_golden():
 
 if __name__ == "__main__":
     signal_golden()
+
+
+def audio_golden():
+    """utils.resample_audio / compute_envelope from the reference's own module on a seeded 0.6 s
+    amplitude-modulated noise burst (stored as float32 so the fixture stays small)."""
+    u = reference_import.load_utils()
+    rng = np.random.default_rng(11)
+    n = 26460
+    t = np.arange(n) / 44100.0
+    audio = ((1 + 0.6 * np.sin(2 * np.pi * 3.1 * t + 0.3)) * rng.standard_normal(n)).astype(np.float32)
+    a64 = audio.astype(np.float64)
+    rs = u.resample_audio(a64)
+    env = u.compute_envelope(rs, 250)
+    odd_in = np.abs(rng.standard_normal(1501)) + 0.2                              # odd length
+    np.savez_compressed(os.path.join(HERE, "audio.npz"), audio=audio, resampled=rs, envelope=env,
+                        odd_input=odd_in, odd_envelope=u.compute_envelope(odd_in, 250))
+    print("audio.npz:", rs.shape, env.shape)
+
+
+if __name__ == "__main__":
+    audio_golden()

@@ -33,3 +33,26 @@ def test_window_dropins_are_pure_slicing():
     assert np.array_equal(a, b) and np.array_equal(ta, tb)
     assert np.array_equal(dsp.create_windows(x[0], 250, 62), signal_ref.create_windows(x[0], 250, 62))
     assert dsp.create_windows(x[0][:100], 250, 62).shape == (0, 250)
+
+
+def test_audio_front_end_matches_reference_fixture():
+    """oracle restatement of resample_audio / compute_envelope vs the reference's own outputs."""
+    A = np.load(os.path.join(os.path.dirname(__file__), "golden", "audio.npz"))
+    rs = signal_ref.resample_audio(A["audio"].astype(np.float64))
+    np.testing.assert_allclose(rs, A["resampled"], rtol=0, atol=1e-13 * np.abs(A["resampled"]).max())
+    np.testing.assert_allclose(signal_ref.compute_envelope(rs, 250), A["envelope"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(signal_ref.compute_envelope(A["odd_input"], 250), A["odd_envelope"], rtol=0, atol=1e-12)
+
+
+def test_resample_design_matches_scipy():
+    """the host-side filter / alignment the CUDA resampler is fed reproduces scipy's upfirdn call"""
+    from scipy import signal
+    from tda_eeg_audio_b200 import audio
+    x = np.random.default_rng(2).standard_normal(5000)
+    for up, down in ((250, 44100), (3, 7), (2, 1), (5, 3)):
+        u, d, hpoly, n_pre, n_out = audio.design_resample(len(x), up, down)
+        h = hpoly.T.reshape(-1)              # h_padded (zero tail)
+        y = signal.upfirdn(h, x, u, d)[n_pre:n_pre + n_out]
+        ref = signal.resample_poly(x, up, down)
+        assert len(ref) == n_out
+        np.testing.assert_allclose(y, ref, rtol=0, atol=1e-13)
