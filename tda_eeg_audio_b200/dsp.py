@@ -199,6 +199,22 @@ def compute_correlation_matrix(window_data):
     return corr[0, 0].cpu().numpy()
 
 
+def correlation_to_distance_batched(corr, method="euclidean"):
+    """corr: CUDA float64 (W, n, n) -> float64 distances (W, n, n), one correlation_to_distance per matrix."""
+    import torch
+    if method not in _METHODS:
+        raise ValueError(f"Unknown method: {method}")
+    _lib.require_cuda()
+    corr = corr.contiguous()
+    d = torch.empty_like(corr)
+    st = torch.cuda.current_stream().cuda_stream
+    lib = _lib.load()
+    for w in range(corr.shape[0]):
+        _lib.check(lib.tda_corr_to_dist_f64(corr[w].data_ptr(), corr.shape[1], _METHODS[method], d[w].data_ptr(), st),
+                   "tda_corr_to_dist_f64")
+    return d
+
+
 def correlation_to_distance(corr_matrix, method="euclidean"):
     import torch
     if method not in _METHODS:

@@ -45,7 +45,8 @@ def select_windows(n_win, max_windows):
 
 
 def audio_diagrams_from_envelope(env, fs=250, bands=None, window_sec=1.0, overlap=0.75, takens_dim=3,
-                                 subsample=2, max_windows=15, thresh=2.0, cap1=256, want_pairs=False):
+                                 subsample=2, max_windows=15, thresh=2.0, cap1=256, want_pairs=False,
+                                 window_idx=None):
     """Envelope (R, T) CUDA float64 -> per band Takens/Rips diagrams of the selected windows.
 
     The audio chain of process_recording (/root/reference/scripts/tda_eeg_audio_comparison.py:57-92)
@@ -65,7 +66,7 @@ def audio_diagrams_from_envelope(env, fs=250, bands=None, window_sec=1.0, overla
     win = int(window_sec * fs)
     step = int(win * (1 - overlap))
     n_win = dsp.n_windows(T, win, step)
-    idx = select_windows(n_win, max_windows)
+    idx = select_windows(n_win, max_windows) if window_idx is None else np.asarray(window_idx, dtype=np.int64)
     n_sel = len(idx)
     ba = [dsp.design_bandpass_ba(*bands[b], fs) for b in names]
     assert all(x is not None for x in ba), "degenerate band (lo >= hi)"

@@ -88,3 +88,71 @@ def audio_golden():
 
 if __name__ == "__main__":
     audio_golden()
+
+
+def names_golden():
+    """the reference's own features/feature_names.txt (column order of X.npy)"""
+    import shutil
+    shutil.copyfile(os.path.join(reference_import.REFERENCE_ROOT, "features", "feature_names.txt"),
+                    os.path.join(HERE, "feature_names.txt"))
+    print("feature_names.txt copied")
+
+
+if __name__ == "__main__":
+    names_golden()
+
+
+def _reference_functions(script, names, namespace):
+    """exec the named top-level function definitions of a reference script where it lies (the
+    scripts themselves cannot be imported: they need seaborn/matplotlib and run their analysis at
+    import time)."""
+    import ast
+    path = os.path.join(reference_import.REFERENCE_ROOT, "scripts", script)
+    tree = ast.parse(open(path).read(), filename=path)
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert {n.name for n in body} == set(names), (script, names)
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), namespace)
+    return namespace
+
+
+def drivers_golden():
+    """process_file_features (tda_eeg_classification_v2.py) and process_recording
+    (tda_eeg_audio_comparison.py) of the reference, run on tests.inputs.tiny_dataset with
+    ripser/persim replaced by the CPU oracle."""
+    import hashlib
+    import json
+    import tempfile
+    from pathlib import Path
+    from scipy.stats import spearmanr
+    from oracle import rips as orips
+    u = reference_import.load_utils()
+    with tempfile.TemporaryDirectory() as td:
+        mat, gdir = inputs.tiny_dataset(td)
+        ns = {"np": np, "hashlib": hashlib, "ripser": orips.ripser}
+        _reference_functions("tda_eeg_classification_v2.py",
+                             ["process_file_features", "compute_persistence_diagram", "extract_persistence_features",
+                              "validate_distance_matrix"], ns)
+        out = {}
+        for tag, kw in (("all", {}), ("rand10", {"max_windows_per_band": 10, "window_sampling": "random"}),
+                        ("first7", {"max_windows_per_band": {"alpha": 7}, "window_sampling": "first"})):
+            feats, meta = ns["process_file_features"](Path(gdir), u.FREQ_BANDS, **kw)
+            out[tag] = {"features": {k: float(v) for k, v in feats.items()},
+                        "n_windows_used": meta["n_windows_used"], "n_windows": meta["n_windows"]}
+        ns2 = {k: getattr(u, k) for k in dir(u) if not k.startswith("_")}
+        ns2.update({"np": np, "spearmanr": spearmanr, "DATA_DIR": Path(td) / "data", "GRAPHS_DIR": Path(td) / "graphs",
+                    "WINDOW_SEC": 1.0, "OVERLAP": 0.75, "MAX_WINDOWS": 15})
+        _reference_functions("tda_eeg_audio_comparison.py", ["process_recording"], ns2)
+        out["process_recording"] = ns2["process_recording"]("S01_trial1.mat", "slow")
+        ns3 = dict(ns2)
+        _reference_functions("matched_vs_mismatched.py", ["get_audio_diagrams", "get_eeg_diagrams",
+                                                          "compute_cross_wasserstein"], ns3)
+        a = ns3["get_audio_diagrams"]("S01_trial1.mat", "slow")
+        e = ns3["get_eeg_diagrams"]("S01_trial1.mat", "slow")
+        out["cross_wasserstein_h1"] = {b: float(ns3["compute_cross_wasserstein"](e[b], a[b])) for b in u.FREQ_BANDS}
+        out["n_audio_diagrams"] = {b: len(a[b]) for b in u.FREQ_BANDS}
+    json.dump(out, open(os.path.join(HERE, "drivers.json"), "w"), indent=1, sort_keys=True)
+    print("drivers.json:", sorted(out), out["process_recording"]["bands"]["alpha"]["wasserstein_h1"])
+
+
+if __name__ == "__main__":
+    drivers_golden()
