@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--recordings", type=int, default=R_REC, help="debug: smaller workload")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the audio / stress-cloud side measurements")
     return ap.parse_args()
 
 
@@ -142,6 +143,36 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
+
+
+def secondary_workloads(dev):
+    """Other BASELINE.json configurations, reported next to the headline (never part of `value`):
+    audio Takens clouds (config c) and the 1,000 / 2,000-point scaling-stress clouds (config e)
+    through the grid-cooperative engine, device-resident distance matrices, CUDA events."""
+    import torch
+    from tda_eeg_audio_b200 import rips_h01_batched
+    from tools.large_bench import takens_clouds
+    out = {}
+    for name, B, n in (("audio_takens_124pt", 8192, 124), ("audio_takens_248pt", 4096, 248),
+                       ("stress_1000pt", 148, 1000), ("stress_2000pt", 64, 2000)):
+        D = takens_clouds(B, n, dev=dev)
+        buf = {}
+        run = lambda: rips_h01_batched(D, THRESH, cap1=4 * n, want_pairs=False, out=buf, engine="large")
+        run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        out[name] = {"clouds": B, "points": n, "ms": round(ms, 3), "diagrams_per_s": round(B / ms * 1e3, 1),
+                     "mean_h1_bars": round(float(buf["counts"][:, 1].float().mean()), 2),
+                     "status_nonzero": int((buf["status"] != 0).sum())}
+        del D, buf
+        torch.cuda.empty_cache()
+    return out
 
 
 def workload_config(args, world):
@@ -310,6 +341,13 @@ def main():
                          f"({dt:.2f} s wall, oracle/rips_cpu.cpp, OpenMP dynamic)",
                "single_thread_value": rate1}
 
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        try:
+            secondary = secondary_workloads(dev)
+        except Exception as exc:  # never lose the headline line to a secondary measurement
+            secondary = {"error": repr(exc)}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -318,6 +356,7 @@ def main():
             "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
             "quality": {"mean_h1_bars": mean_h1, "h1_truncated_windows": trunc, "internal_overflow": bad},
+            "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -39,26 +39,36 @@ def timed(fn, n=3, warm=1):
     return e0.elapsed_time(e1) / n
 
 
-cases = [("large", 64, 1000, 2.0), ("large", 64, 1500, 2.0), ("large", 64, 2000, 2.0), ("large", 64, 2000, 0.25),
-         ("large", 296, 1000, 2.0), ("large", 8192, 124, 2.0), ("medium", 8192, 124, 2.0), ("large", 8192, 248, 2.0), ("medium", 8192, 248, 2.0)]
-if len(sys.argv) > 1:
-    cases = [c for c in cases if c[0] in sys.argv[1:]]
-for engine, B, n, thr in cases:
-    D = takens_clouds(B, n)
-    out = {}
-    cap1 = 4 * n
-    ms = timed(lambda: rips_h01_batched(D, thr, cap1=cap1, want_pairs=True, out=out, engine=engine))
-    parts = {}
-    if engine == "large":
-        _lib.profile_enable(True)
-        rips_h01_batched(D, thr, cap1=cap1, want_pairs=True, out=out, engine=engine)
-        torch.cuda.synchronize()
-        for k in ("keys", "sort", "scatter", "kruskal", "classify", "sweep_t1", "sweep_t2"):
-            parts[k] = round(_lib.profile_query("rips_large_" + k)[0], 3)
-        _lib.profile_enable(False)
-    c = out["counts"]
-    print(json.dumps({"engine": engine, "B": B, "N": n, "thresh": thr, "ms": round(ms, 3), "clouds_per_s": round(B / ms * 1e3, 1),
-                      "mean_h1": float(c[:, 1].float().mean()), "max_h1": int(c[:, 1].max()),
-                      "status_nonzero": int((out["status"] != 0).sum()), "kernel_ms": parts}), flush=True)
-    del D, out
-    torch.cuda.empty_cache()
+CASES = [("large", 64, 1000, 2.0), ("large", 64, 1500, 2.0), ("large", 64, 2000, 2.0), ("large", 64, 2000, 0.25),
+         ("large", 296, 1000, 2.0), ("large", 8192, 124, 2.0), ("medium", 8192, 124, 2.0), ("large", 8192, 248, 2.0),
+         ("medium", 8192, 248, 2.0)]
+
+
+def main():
+    cases = CASES
+    if len(sys.argv) > 1:
+        cases = [c for c in cases if c[0] in sys.argv[1:]]
+    for engine, B, n, thr in cases:
+        D = takens_clouds(B, n)
+        out = {}
+        cap1 = 4 * n
+        ms = timed(lambda: rips_h01_batched(D, thr, cap1=cap1, want_pairs=True, out=out, engine=engine))
+        parts = {}
+        if engine == "large":
+            _lib.profile_enable(True)
+            rips_h01_batched(D, thr, cap1=cap1, want_pairs=True, out=out, engine=engine)
+            torch.cuda.synchronize()
+            for k in ("keys", "sort", "scatter", "kruskal", "classify", "sweep_t1", "sweep_t2"):
+                parts[k] = round(_lib.profile_query("rips_large_" + k)[0], 3)
+            _lib.profile_enable(False)
+        c = out["counts"]
+        print(json.dumps({"engine": engine, "B": B, "N": n, "thresh": thr, "ms": round(ms, 3),
+                          "clouds_per_s": round(B / ms * 1e3, 1), "mean_h1": float(c[:, 1].float().mean()),
+                          "max_h1": int(c[:, 1].max()), "status_nonzero": int((out["status"] != 0).sum()),
+                          "kernel_ms": parts}), flush=True)
+        del D, out
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
