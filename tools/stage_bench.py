@@ -65,12 +65,14 @@ for sub in (2, 1):
         aud.update(pipeline.audio_diagrams_from_envelope(env, overlap=0.0, subsample=sub, max_windows=None, cap1=256))
     ms_all = timed(audio, n=2, warm=1)
     Dm, npts = aud["D"], aud["npts"]
-    out = {}
-    ms = timed(lambda: rips_h01_batched(Dm, thresh=2.0, cap1=256, want_pairs=False, npts=npts, engine="medium", out=out), n=2, warm=1)
-    ov = out["ws"][:8].view(torch.int32)[:2].tolist()
+    out, outm = {}, {}
+    ms = timed(lambda: rips_h01_batched(Dm, thresh=2.0, cap1=256, want_pairs=False, npts=npts, engine="large", out=out), n=2, warm=1)
+    msm = timed(lambda: rips_h01_batched(Dm, thresh=2.0, cap1=256, want_pairs=False, npts=npts, engine="medium", out=outm), n=2, warm=1)
+    same = bool(torch.equal(out["counts"], outm["counts"]))
     print(json.dumps({"stage": f"audio Takens sub={sub}", "clouds": Dm.shape[0], "npts_mean": float(npts.float().mean()),
-                      "npts_max": int(npts.max()), "chain_ms": ms_all, "rips_ms": ms, "clouds_per_s": Dm.shape[0] / ms * 1e3,
-                      "mean_h1": float(out["counts"][:, 1].float().mean()), "tier_overflow": ov,
+                      "npts_max": int(npts.max()), "chain_ms": ms_all, "rips_large_ms": ms, "rips_medium_ms": msm,
+                      "clouds_per_s": Dm.shape[0] / ms * 1e3, "engines_agree": same,
+                      "mean_h1": float(out["counts"][:, 1].float().mean()),
                       "status_bad": int((out["status"] & 4).sum())}))
     if sub == 2:
         eeg = st["rips"]
@@ -80,6 +82,16 @@ for sub in (2, 1):
         ms1 = timed(lambda: wasserstein_batched(eeg["bd1"][:nB], e_c[:, 1], out["bd1"][:nB], out["counts"][:nB, 1]), n=2, warm=1)
         print(json.dumps({"stage": "wasserstein", "pairs": nB, "H0_ms": ms0, "H0_pairs_per_s": nB / ms0 * 1e3,
                           "H1_ms": ms1, "H1_pairs_per_s": nB / ms1 * 1e3}))
+# audio front end
+from tda_eeg_audio_b200 import audio as _audio
+xa = torch.randn((min(R, 64), 2646000), generator=g, device=dev, dtype=torch.float64)
+ms = timed(lambda: _audio.resample_poly_batched(xa, 250, 44100), n=3, warm=1)
+print(json.dumps({"stage": "resample_poly 44.1k->250", "recordings": xa.shape[0], "ms": ms,
+                  "fp64_TFLOPs": xa.shape[0] * 15000 * 3529 * 2 / ms / 1e9, "input_GBps": xa.numel() * 8 / ms / 1e6}))
+ya = _audio.resample_poly_batched(xa, 250, 44100)
+ms = timed(lambda: _audio.compute_envelope_batched(ya, 250), n=3, warm=1)
+print(json.dumps({"stage": "hilbert envelope + LP50", "recordings": xa.shape[0], "ms": ms}))
+del xa
 # CPU baselines for the audio clouds (bounded sample)
 try:
     from oracle import rips as orips
