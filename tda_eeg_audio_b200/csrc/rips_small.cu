@@ -33,44 +33,11 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "rips_small.cuh"
 #include "tda_b200.h"
 
 namespace tda {
 namespace rips_small {
-
-constexpr int kMaxN = 64;
-constexpr uint32_t kFull = 0xFFFFFFFFu;
-constexpr uint32_t kEssential = 0xFFFFFFFFu;
-// P[rank] = j | i << 6 | flags
-constexpr uint32_t kMst = 1u << 12;      // edge merges two components (H0 death)
-constexpr uint32_t kTie = 1u << 13;      // the next edge in the order has the same length
-constexpr uint32_t kTiePrev = 1u << 14;  // the previous edge in the order has the same length
-__device__ __forceinline__ int p_i(uint32_t p) { return (p >> 6) & 63; }
-__device__ __forceinline__ int p_j(uint32_t p) { return p & 63; }
-
-struct Params {
-    const float* D;
-    long long strideB;
-    int ld, N, B;
-    float thresh;
-    float* bd0;
-    long long* pr0;
-    float* bd1;
-    long long* pr1;
-    int* counts;
-    int* status;
-    int cap1;
-    const int* worklist;   // nullptr => every window 0..B-1
-    const int* n_work;     // device counter with the length of worklist
-    int* overflow_list;    // nullptr on the last tier
-    int* n_overflow;
-    uint32_t* phi_global;  // per-warp PHI scratch (PHI_GLOBAL tiers), E*W words per warp
-    uint32_t* rec_global;  // per-warp record scratch (PHI_GLOBAL tiers), 4*R words per warp
-    uint8_t* defv_global;  // per-warp tie-run scratch, Epad bytes per warp (all tiers)
-};
-
-__host__ __device__ inline int c2(int i) { return i * (i - 1) / 2; }
-__host__ __device__ inline int c3(int i) { return i * (i - 1) * (i - 2) / 6; }
 
 template <int W, bool PHI_GLOBAL> struct Layout {
     // all sizes in bytes, per warp
@@ -105,24 +72,6 @@ template <int W, bool PHI_GLOBAL> struct Layout {
         return a16(s);
     }
 };
-
-__device__ __forceinline__ uint32_t lanemask_lt() {
-    uint32_t m;
-    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
-    return m;
-}
-__device__ __forceinline__ uint32_t float_key(float d) {
-    uint32_t u = __float_as_uint(d);
-    return (u >> 31) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float key_float(uint32_t k) {
-    uint32_t u = (k >> 31) ? (k & 0x7FFFFFFFu) : ~k;
-    return __uint_as_float(u);
-}
-__device__ __forceinline__ int tri_index(int x, int y, int z) {
-    const int a = max(x, max(y, z)), c = min(x, min(y, z)), b = x + y + z - a - c;
-    return c3(a) + c2(b) + c;
-}
 
 template <int W, bool PHI_GLOBAL, int NT> struct Warp {
     typedef Layout<W, PHI_GLOBAL> L;
@@ -866,32 +815,42 @@ extern "C" int tda_rips_h01_batched(const float* D, int B, int N, int ld, long l
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms > 148) sms = 148;
-    // tier 1: W=2, shared-memory PHI, 4 warps per CTA, as many CTAs per SM as shared memory allows
-    {
+    // TDA_RIPS_ENGINE=bits selects the alternative tiers 1-2 of rips_bits.cu (lane = class bit-matrix
+    // sweep: a second, independently written implementation, parity-tested, ~8 % slower on EEG windows)
+    const char* eng = getenv("TDA_RIPS_ENGINE");
+    if (!(eng && eng[0] == 'b')) {
+        // tiers 1-2: PHI per edge, lanes = apexes
+        {
+            p.worklist = nullptr; p.n_work = nullptr;
+            p.overflow_list = (int*)(w8 + wl.list1); p.n_overflow = counters + 0;
+            int wpb = (int)(((227 * 1024) / 2 - 1024) / Layout<2, false>::bytes(N));
+            if (wpb < 1) wpb = 1;
+            if (wpb > 8) wpb = 8;
+            size_t smem = Layout<2, false>::bytes(N) * wpb;
+            int per_sm = (int)((227 * 1024) / (smem + 1024));
+            if (per_sm < 1) per_sm = 1;
+            if (per_sm > 2) per_sm = 2;
+            long long need = ((long long)B + wpb - 1) / wpb;
+            int grid = (int)((long long)sms * per_sm < need ? (long long)sms * per_sm : need);
+            e = (N == 47) ? launch_tier<2, false, 47>(p, wpb, grid, st) : launch_tier<2, false, 0>(p, wpb, grid, st);
+            if (e != cudaSuccess) return (int)e;
+        }
+        {
+            p.worklist = (const int*)(w8 + wl.list1); p.n_work = counters + 0;
+            p.overflow_list = (int*)(w8 + wl.list2); p.n_overflow = counters + 1;
+            e = launch_tier<4, false, 0>(p, 2, sms * 2, st);
+            if (e != cudaSuccess) return (int)e;
+        }
+    } else {
+        // tier 1: class-per-lane bit-matrix sweep, 32 simultaneous classes (rips_bits.cu)
         p.worklist = nullptr; p.n_work = nullptr;
         p.overflow_list = (int*)(w8 + wl.list1); p.n_overflow = counters + 0;
-        // two CTAs per SM, each with as many warps as shared memory allows (<= 8: kMaxWarps)
-        int wpb = (int)(((227 * 1024) / 2 - 1024) / Layout<2, false>::bytes(N));
-        if (wpb < 1) wpb = 1;
-        if (wpb > 8) wpb = 8;
-        int max_per_sm = 2;
-        if (const char* ev = getenv("TDA_RIPS_WPB")) { int v = atoi(ev); if (v >= 1 && v <= 8) wpb = v; }   // tuning knobs
-        if (const char* ev = getenv("TDA_RIPS_CTAS")) { int v = atoi(ev); if (v >= 1 && v <= 16) max_per_sm = v; }
-        size_t smem = Layout<2, false>::bytes(N) * wpb;
-        int per_sm = (int)((227 * 1024) / (smem + 1024));
-        if (per_sm < 1) per_sm = 1;
-        if (per_sm > max_per_sm) per_sm = max_per_sm;
-        if (per_sm * wpb > 16) per_sm = 16 / wpb;
-        long long need = ((long long)B + wpb - 1) / wpb;
-        int grid = (int)((long long)sms * per_sm < need ? (long long)sms * per_sm : need);
-        e = (N == 47) ? launch_tier<2, false, 47>(p, wpb, grid, st) : launch_tier<2, false, 0>(p, wpb, grid, st);
+        e = launch_bits_tier(p, 1, sms, st);
         if (e != cudaSuccess) return (int)e;
-    }
-    // tier 2: W=4 on the windows tier 1 gave up on
-    {
+        // tier 2: the same with 64 classes on the windows tier 1 gave up on
         p.worklist = (const int*)(w8 + wl.list1); p.n_work = counters + 0;
         p.overflow_list = (int*)(w8 + wl.list2); p.n_overflow = counters + 1;
-        e = launch_tier<4, false, 0>(p, 2, sms * 2, st);
+        e = launch_bits_tier(p, 2, sms, st);
         if (e != cudaSuccess) return (int)e;
     }
     // tier 3: W=64 with PHI in global scratch, handles every N<=64 input

@@ -1,0 +1,68 @@
+// rips_small.cuh — declarations shared by the two kernel families of the N <= 64 Rips engine
+// (rips_bits.cu: class-per-lane bit-matrix sweep, tiers 1-2; rips_small.cu: PHI-per-edge sweep,
+// the capacity tier that handles every input).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tda {
+namespace rips_small {
+
+constexpr int kMaxN = 64;
+constexpr uint32_t kFull = 0xFFFFFFFFu;
+constexpr uint32_t kEssential = 0xFFFFFFFFu;
+// P[rank] = j | i << 6 | flags
+constexpr uint32_t kMst = 1u << 12;      // edge merges two components (H0 death)
+constexpr uint32_t kTie = 1u << 13;      // the next edge in the order has the same length
+constexpr uint32_t kTiePrev = 1u << 14;  // the previous edge in the order has the same length
+__device__ __forceinline__ int p_i(uint32_t p) { return (p >> 6) & 63; }
+__device__ __forceinline__ int p_j(uint32_t p) { return p & 63; }
+
+struct Params {
+    const float* D;
+    long long strideB;
+    int ld, N, B;
+    float thresh;
+    float* bd0;
+    long long* pr0;
+    float* bd1;
+    long long* pr1;
+    int* counts;
+    int* status;
+    int cap1;
+    const int* worklist;   // nullptr => every window 0..B-1
+    const int* n_work;     // device counter with the length of worklist
+    int* overflow_list;    // nullptr on the last tier
+    int* n_overflow;
+    uint32_t* phi_global;  // per-warp PHI scratch (PHI_GLOBAL tiers), E*W words per warp
+    uint32_t* rec_global;  // per-warp record scratch (PHI_GLOBAL tiers), 4*R words per warp
+    uint8_t* defv_global;  // per-warp tie-run scratch, Epad bytes per warp (all tiers)
+};
+
+__host__ __device__ inline int c2(int i) { return i * (i - 1) / 2; }
+__host__ __device__ inline int c3(int i) { return i * (i - 1) * (i - 2) / 6; }
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+__device__ __forceinline__ uint32_t float_key(float d) {
+    uint32_t u = __float_as_uint(d);
+    return (u >> 31) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+    uint32_t u = (k >> 31) ? (k & 0x7FFFFFFFu) : ~k;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ int tri_index(int x, int y, int z) {
+    const int a = max(x, max(y, z)), c = min(x, min(y, z)), b = x + y + z - a - c;
+    return c3(a) + c2(b) + c;
+}
+
+// tiers 1-2 (rips_bits.cu): cpl = classes per lane (1 => 32 simultaneous classes, 2 => 64)
+cudaError_t launch_bits_tier(const Params& p, int cpl, int sms, cudaStream_t st);
+size_t bits_tier_warp_bytes(int N, int cpl);
+
+}  // namespace rips_small
+}  // namespace tda

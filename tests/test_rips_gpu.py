@@ -142,3 +142,20 @@ def test_ripser_shim(cuda):
         assert np.array_equal(a["pairs"][k], b["pairs"][k])
     with pytest.raises(Exception, match="not square"):
         ripser(np.zeros((3, 4)), distance_matrix=True)
+
+
+def test_alternative_class_per_lane_tiers(cuda, monkeypatch):
+    """TDA_RIPS_ENGINE=bits: the lane = class bit-matrix sweep of rips_bits.cu (a second, independently
+    written implementation of tiers 1-2) under the same bit-exact bar."""
+    monkeypatch.setenv("TDA_RIPS_ENGINE", "bits")
+    rng = np.random.default_rng(21)
+    g, _ = _compare(inputs.eeg_like(rng, 256), 2.0)
+    assert (g["status"] == 0).all()
+    _compare(inputs.sym_uniform(rng, 128, 47), 2.0)          # > 32 and > 64 simultaneous classes: all three tiers
+    for n in (3, 33, 47, 64):
+        D = inputs.sym_uniform(rng, 32, n)
+        _compare(D, np.inf)
+        _compare(D, 0.5)
+        _compare((np.round(D * 8) / 8).astype(np.float32), np.inf)
+    _compare(inputs.circle_cloud(rng, 32, 40), 0.9)
+    _compare(np.ones((2, 47, 47), np.float32) - np.eye(47, dtype=np.float32), 2.0)
