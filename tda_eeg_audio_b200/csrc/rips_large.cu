@@ -16,7 +16,7 @@
 //                Ripser's tie-break)
 //   K2 scatter   sorted position r -> P[r] = (i, j, tie flag), rank matrix T[i][j] = r
 //   K3 kruskal   one CTA per cloud: MST flags + the H0 pairs (elder rule for the vertex)
-//   K4 classify  one warp per edge, cooperative over the whole grid: the first cofacet of every
+//   K4 classify  one thread per edge, cooperative over the whole grid: the first cofacet of every
 //                non-MST edge (largest apex v with T[i][v], T[j][v] inside the edge's tie run or
 //                before it).  If that triangle has the edge as its youngest edge the two form an
 //                apparent zero-persistence pair (defv = v) — >99 % of all columns end here —
@@ -270,61 +270,50 @@ template <int NTH> __global__ void __launch_bounds__(NTH) kruskal_kernel(Params 
 }
 
 // ------------------------------------------------------------------------------------ K4 classify
-// one warp per block of 32 consecutive ranks; the non-MST ones are classified one after the other
+// one THREAD per edge: walk the apexes downwards, four ranks per load, until the first cofacet.
+// Lanes of a warp hold consecutive ranks, i.e. edges of nearly equal length whose neighbourhoods
+// are equally dense, so their scans have similar lengths (~2 sqrt(N) on average: most edges are
+// late and find an apex within the first few candidates).
 __global__ void __launch_bounds__(256) classify_kernel(Params p) {
-    const int lane = threadIdx.x & 31;
-    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
-    const long long blocks_per_cloud = (p.Emax + 31) / 32;
-    for (long long w = gw; w < blocks_per_cloud * p.C; w += nwarp) {
-        const int c = (int)(w / blocks_per_cloud);
-        const int rb = (int)(w - (long long)c * blocks_per_cloud) * 32;
-        const int m = p.m[c];
-        if (rb >= m) continue;
-        const int n = cloud_n(p, p.c0 + c);
+    const long long total = p.Emax * p.C;
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(w / p.Emax);
+        const int r = (int)(w - (long long)c * p.Emax);
+        if (r >= p.m[c]) continue;
         uint32_t* Pc = p.P + (size_t)c * p.Emax;
+        const uint32_t q = Pc[r];
+        if (q & kMst) continue;
+        const int n = cloud_n(p, p.c0 + c);
         const uint32_t* Tc = p.T + (size_t)c * p.N * p.ldT;
         const uint64_t* keys = p.keysB + (size_t)c * p.Emax;
-        const int rr = rb + lane;
-        const uint32_t pe = rr < m ? Pc[rr] : kMst;
-        const uint32_t pprev = (rr > 0 && rr < m) ? Pc[rr - 1] : 0u;
-        uint32_t todo = __ballot_sync(kFull, !(pe & kMst));
-        const int top0 = (n - 1) & ~31;
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const uint32_t q = __shfl_sync(kFull, pe, src);
-            const uint32_t qprev = __shfl_sync(kFull, pprev, src);
-            const int r = rb + src;
-            const int i = p_i(q), j = p_j(q);
-            const bool tied = (q & kTieNext) || (qprev & kTieNext);
-            const uint32_t k32r = tied ? (uint32_t)(keys[r] >> p.ib) : 0u;
-            const uint32_t* Ti = Tc + (size_t)i * p.ldT;
-            const uint32_t* Tj = Tc + (size_t)j * p.ldT;
-            int dv = -1;
-            for (int v0 = top0; v0 >= 0; v0 -= 32) {
-                const int v = v0 + lane;
-                uint32_t ta = kInf, tb = kInf;
-                if (v < n) { ta = Ti[v]; tb = Tj[v]; }
-                bool ina = ta < (uint32_t)r, inb = tb < (uint32_t)r;
+        const int i = p_i(q), j = p_j(q);
+        const bool tied = (q & kTieNext) || (r > 0 && (Pc[r - 1] & kTieNext));
+        const uint32_t k32r = tied ? (uint32_t)(keys[r] >> p.ib) : 0u;
+        const uint4* Ti = reinterpret_cast<const uint4*>(Tc + (size_t)i * p.ldT);
+        const uint4* Tj = reinterpret_cast<const uint4*>(Tc + (size_t)j * p.ldT);
+        int dv = -1;
+        bool found = false;
+        for (int v4 = (n - 1) >> 2; v4 >= 0 && !found; --v4) {
+            const uint4 a4 = __ldg(Ti + v4), b4 = __ldg(Tj + v4);
+            const uint32_t ta[4] = {a4.x, a4.y, a4.z, a4.w}, tb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int k = 3; k >= 0; --k) {
+                if (found || 4 * v4 + k >= n) continue;
+                bool ina = ta[k] < (uint32_t)r, inb = tb[k] < (uint32_t)r;
                 const bool strict = ina && inb;
                 if (tied) {
-                    if (!ina && ta != kInf && ta > (uint32_t)r) ina = (uint32_t)(keys[ta] >> p.ib) == k32r;
-                    if (!inb && tb != kInf && tb > (uint32_t)r) inb = (uint32_t)(keys[tb] >> p.ib) == k32r;
+                    // an edge of the same tie run that comes later in the order is present too
+                    if (!ina && ta[k] != kInf && ta[k] > (uint32_t)r) ina = (uint32_t)(keys[ta[k]] >> p.ib) == k32r;
+                    if (!inb && tb[k] != kInf && tb[k] > (uint32_t)r) inb = (uint32_t)(keys[tb[k]] >> p.ib) == k32r;
                 }
-                const uint32_t bal = __ballot_sync(kFull, ina && inb);
-                if (bal) {
-                    const int sl = 31 - __clz(bal);
-                    const bool yes = __shfl_sync(kFull, strict, sl);
-                    dv = yes ? v0 + sl : -1;
-                    break;
+                if (ina && inb) {
+                    found = true;
+                    dv = strict ? 4 * v4 + k : -1;   // the first cofacet must have the edge as youngest edge
                 }
-            }
-            if (lane == 0) {
-                if (dv < 0) Pc[r] = q | kBirth;
-                else p.defv[(size_t)c * p.Emax + r] = (uint16_t)dv;
             }
         }
+        if (dv < 0) Pc[r] = q | kBirth;
+        else p.defv[(size_t)c * p.Emax + r] = (uint16_t)dv;
     }
 }
 
@@ -826,8 +815,10 @@ constexpr int kSms = 148;  // B200; grids and the workspace layout are sized for
 // resident sweep CTAs per SM on the first tier (threads and shared memory)
 static int tier1_ctas_per_sm(int N, int nth) {
     int by_threads = 2048 / nth;
+    if (by_threads > 32) by_threads = 32;  // resident CTAs per SM
     int by_smem = (int)((227 * 1024) / ((N > 1024 ? sweep_smem<16>(N, false) : sweep_smem<8>(N, false)) + 1024));
     int r = by_threads < by_smem ? by_threads : by_smem;
+    if (N > 256 && r > 2) r = 2;  // ~128 registers per thread with several apexes per thread
     return r < 1 ? 1 : r;
 }
 
@@ -836,8 +827,8 @@ static bool make_plan(int B, int N, size_t ws_bytes, Plan& pl) {
     pl.ldT = (N + 31) & ~31;
     pl.Emax = c2(N);
     pl.ib = bits_for(pl.Emax);
-    pl.nth = N <= 128 ? 128 : (N <= 256 ? 256 : 1024);
-    pl.apt = N <= 1024 ? 1 : 2;
+    pl.nth = N <= 128 ? 32 : (N <= 256 ? 64 : 256);
+    pl.apt = N <= 256 ? 4 : (N <= 512 ? 2 : (N <= 1024 ? 4 : 8));
     long long cp = 64ll * N;
     pl.capP = (int)(cp < kCapPMax ? cp : kCapPMax);
     pl.capR = (int)(pl.Emax < kCapRMax ? (pl.Emax < 64 ? 64 : pl.Emax) : kCapRMax);
@@ -906,7 +897,7 @@ static cudaError_t launch_sweeps(Params p, const Plan& pl, char* w8, cudaStream_
         p.worklist = (const int*)(w8 + pl.list); p.n_work = counters;
         p.overflow_list = nullptr; p.n_overflow = nullptr;
         p.phic = (uint32_t*)(w8 + pl.phic2);
-        constexpr bool SG = (APT > 1);
+        constexpr bool SG = (APT > 4);
         const size_t smem = sweep_smem<32>(p.N, SG);
         e = cudaFuncSetAttribute(sweep_kernel<NTH, APT, 32, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -999,17 +990,19 @@ extern "C" int tda_rips_h01_large(const float* D, const int* npts, int B, int N,
         }
         {
             ProfScope prof("rips_large_classify", st);
-            long long warps = ((pl.Emax + 31) / 32) * C;
-            long long blocks = (warps + 7) / 8;
+            long long blocks = (pl.Emax * C + 255) / 256;
             if (blocks > 148 * 64) blocks = 148 * 64;
             classify_kernel<<<(unsigned)blocks, 256, 0, st>>>(p);
             count_launch();
             if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
         }
-        if (N <= 128) e = launch_sweeps<128, 1, 8>(p, pl, w8, st);
-        else if (N <= 256) e = launch_sweeps<256, 1, 8>(p, pl, w8, st);
-        else if (N <= 1024) e = launch_sweeps<1024, 1, 8>(p, pl, w8, st);
-        else e = launch_sweeps<1024, 2, 16>(p, pl, w8, st);
+        // 256 threads whatever the size (block barriers are what a visited edge pays for), 1-8 apexes each
+        // (small clouds: one or two warps per cloud, the visited edges are issue-bound there)
+        if (N <= 128) e = launch_sweeps<32, 4, 8>(p, pl, w8, st);
+        else if (N <= 256) e = launch_sweeps<64, 4, 8>(p, pl, w8, st);
+        else if (N <= 512) e = launch_sweeps<256, 2, 8>(p, pl, w8, st);
+        else if (N <= 1024) e = launch_sweeps<256, 4, 8>(p, pl, w8, st);
+        else e = launch_sweeps<256, 8, 16>(p, pl, w8, st);
         if (e != cudaSuccess) return (int)e;
     }
     return 0;
