@@ -37,6 +37,7 @@
 //   (W = 32) through a device-side hand-over list.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -819,6 +820,8 @@ static int tier1_ctas_per_sm(int N, int nth) {
     int by_smem = (int)((227 * 1024) / ((N > 1024 ? sweep_smem<16>(N, false) : sweep_smem<8>(N, false)) + 1024));
     int r = by_threads < by_smem ? by_threads : by_smem;
     if (N > 256 && r > 2) r = 2;  // ~128 registers per thread with several apexes per thread
+    if (nth == 64 && r > 12) r = 12;  // measured: 129-256 points run best with 12 two-warp CTAs per SM
+    if (const char* ev = getenv("TDA_LARGE_CTAS")) { int v = atoi(ev); if (v >= 1 && v < r) r = v; }   // tuning knob
     return r < 1 ? 1 : r;
 }
 
