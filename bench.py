@@ -57,11 +57,16 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.first = 0
+
+    def mark(self):
+        """samples taken before this call (spin-up under load) are not part of the timed region"""
+        self.first = len(self.lines)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -83,7 +88,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[self.first:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -239,9 +244,14 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        t_spin = time.perf_counter()
+        while time.perf_counter() - t_spin < 0.6:        # nvidia-smi needs a moment before its first sample;
+            step()                                       # keep the GPU under the same load meanwhile (untimed)
+            torch.cuda.synchronize()
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark()
     e0.record()
     for _ in range(args.steps):
         step()
@@ -277,8 +287,21 @@ def main():
     alg_bytes = 4.0 * N * N * B + 16.0 * n_bars   # 4 N^2 + 16 (n_H0 + n_H1) per diagram
     k_avg_ms = k_ms / max(k_n, 1)
     achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9 if k_avg_ms > 0 else 0.0
+    # DRAM traffic and instruction count of the same launch from the committed ncu capture
+    traffic = issue = None
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_rips_small_v3_bench_ncu.json")))
+        traffic = ncu["traffic_bytes"] * B / ncu["windows"]
+        sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+        slots = 148 * 4 * sm_mhz * 1e6                      # warp-instruction issue slots per second
+        ips = ncu["warp_instructions_per_window"] * B / (k_avg_ms * 1e-3)
+        issue = {"bound": "issue slots (148 SMs x 4 schedulers x sm clock)", "achieved": ips, "peak": slots,
+                 "unit": "warp-instructions/s", "frac": ips / slots,
+                 "source": "profiles/r01_rips_small_v3_bench_ncu.json (smsp__inst_executed.sum of the same launch)"}
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "rips_small_kernel<2,false>", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "issue_roofline": issue,
                 "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s",
                 "kernel_ms": k_avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms_per_step": parts,
