@@ -244,10 +244,11 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        t_spin = time.perf_counter()
-        while time.perf_counter() - t_spin < 0.6:        # nvidia-smi needs a moment before its first sample;
-            step()                                       # keep the GPU under the same load meanwhile (untimed)
-            torch.cuda.synchronize()
+    # nvidia-smi needs a moment before its first sample: keep the GPU under the same load meanwhile.
+    # A FIXED number of untimed steps on EVERY rank (step() contains a collective when world > 1).
+    for _ in range(12):
+        step()
+    torch.cuda.synchronize()
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
