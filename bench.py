@@ -159,7 +159,7 @@ def secondary_workloads(dev):
     from tools.large_bench import takens_clouds
     out = {}
     for name, B, n in (("audio_takens_124pt", 8192, 124), ("audio_takens_248pt", 4096, 248),
-                       ("stress_1000pt", 148, 1000), ("stress_2000pt", 64, 2000)):
+                       ("stress_1000pt", 296, 1000), ("stress_2000pt", 148, 2000)):
         D = takens_clouds(B, n, dev=dev)
         buf = {}
         run = lambda: rips_h01_batched(D, THRESH, cap1=4 * n, want_pairs=False, out=buf, engine="large")
