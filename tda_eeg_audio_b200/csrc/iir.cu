@@ -12,7 +12,7 @@
 //
 // Mapping: one thread owns one (band, sequence) job — the recursion is serial in time, and at the
 // benchmark shape there are 332,760 independent jobs.  A CTA of 128 jobs moves time tiles of 32
-// samples through shared memory so that every HBM access is a coalesced 256-byte row segment
+// samples (now 16) through shared memory so that every HBM access is a coalesced 128-byte row segment
 // (lanes along time on the way in/out, lanes along jobs inside the recursion; odd row stride keeps
 // both conflict-free).  The forward pass materialises the padded intermediate once (workspace);
 // the backward pass walks the same tiles in reverse and writes only the un-padded samples.
@@ -26,7 +26,8 @@ namespace tda {
 namespace iir {
 
 constexpr int kJobs = 128;   // threads per CTA = jobs per CTA
-constexpr int kTT = 32;      // samples per time tile
+constexpr int kTT = 16;      // samples per time tile (16: 34 KB of staging per CTA -> 6 CTAs = 24 warps per SM)
+constexpr int kRPW = 32 / kTT;  // tile rows one warp moves per step
 constexpr int kLd = kTT + 1; // odd row stride
 constexpr int kMaxBands = 8;
 constexpr int kMaxSec = 4;   // sos sections
@@ -118,15 +119,16 @@ __global__ void __launch_bounds__(kJobs) iir_pass_kernel(const double* __restric
             const long long tile = BACKWARD ? (n_tiles - 1 - q) : q;
             const long long k0 = tile * kTT;
             // ---- cooperative coalesced load: warp w takes rows w, w+4, ... ; lanes along time
-            for (int r = warp; r < kJobs; r += kJobs / 32) {
+            for (int r = warp * kRPW + lane / kTT; r < kJobs; r += (kJobs / 32) * kRPW) {
                 const long long jb = job0 + r;
-                const long long k = k0 + lane;
+                const int c = lane % kTT;
+                const long long k = k0 + c;
                 double v = 0.0;
                 if (jb < n_jobs && k < Text) {
                     if (!BACKWARD) v = ext_value(in + (jb % n_seq) * x_stride, T, edge, k);
                     else v = in[jb * Text + k];
                 }
-                tin[r * kLd + lane] = v;
+                tin[r * kLd + c] = v;
             }
             __syncthreads();
             // ---- serial recursion, one job per thread
@@ -140,12 +142,13 @@ __global__ void __launch_bounds__(kJobs) iir_pass_kernel(const double* __restric
             }
             __syncthreads();
             // ---- cooperative coalesced store
-            for (int r = warp; r < kJobs; r += kJobs / 32) {
+            for (int r = warp * kRPW + lane / kTT; r < kJobs; r += (kJobs / 32) * kRPW) {
                 const long long jb = job0 + r;
-                const long long k = k0 + lane;
+                const int c = lane % kTT;
+                const long long k = k0 + c;
                 if (jb < n_jobs && k < Text) {
-                    if (!BACKWARD) out[jb * Text + k] = tout[r * kLd + lane];
-                    else if (k >= edge && k < edge + T) out[jb * T + (k - edge)] = tout[r * kLd + lane];
+                    if (!BACKWARD) out[jb * Text + k] = tout[r * kLd + c];
+                    else if (k >= edge && k < edge + T) out[jb * T + (k - edge)] = tout[r * kLd + c];
                 }
             }
             // tin/tout of the next tile are written only after the next __syncthreads pair
@@ -199,7 +202,7 @@ extern "C" int tda_filtfilt_f64(const double* x, long long n_seq, long long T, l
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long n_jobs = n_seq * n_bands;
     long long blocks = (n_jobs + kJobs - 1) / kJobs;
-    const long long maxb = (long long)sms * 3;  // 66 KB static smem per CTA -> 3 CTAs per SM
+    const long long maxb = (long long)sms * 6;  // 34 KB of staging per CTA -> 6 CTAs per SM
     if (blocks > maxb) blocks = maxb;
     cudaStream_t st = (cudaStream_t)stream;
     double* mid = (double*)ws;

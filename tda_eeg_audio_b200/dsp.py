@@ -121,7 +121,7 @@ def corrdist_windows(x, win, step, method="euclidean", out=None, want_corr=False
 
 
 def eeg_distances_from_raw(x, fs=250, bands=FREQ_BANDS, window_size=1.0, overlap=0.75, order=4,
-                           rec_chunk=64, out=None):
+                           rec_chunk=256, out=None):
     """Raw EEG (R, C, T) CUDA float64 -> correlation-distance matrices (R, n_bands, W, C, C) float32:
     notebooks 1 + 2 of the reference for a whole dataset (band-pass sos filtfilt, 1 s windows,
     corrcoef, sqrt(2(1-r)))."""
