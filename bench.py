@@ -349,6 +349,7 @@ def main():
     e2e_ok = bool(torch.equal(h_table.to(dev), res["table"]))
     e2e = {"value": world * B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": e2e_s * 1e3, "matches_device_path": e2e_ok,
+           "h2d_gbs": h2d / e2e_s / 1e9, "note": "bound by the host->device copy of the matrices over PCIe",
            "api": "tda_eeg_features_host (C-ABI, pinned host buffers, 3-stream chunk pipeline)"}
 
     # ---- CPU baseline on a bounded sample of the same matrices (rank 0, N=1 only)
