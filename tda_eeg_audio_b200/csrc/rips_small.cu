@@ -744,6 +744,14 @@ __global__ void __launch_bounds__(256, 1) rips_small_kernel(Params p) {
     const int total = p.worklist ? *p.n_work : p.B;
     for (int t = gw; t < total; t += nw) {
         const int b = p.worklist ? p.worklist[t] : t;
+        if (t + nw < total) {
+            // the next window's matrix starts its way from HBM to L2 now: the key phase of a window is
+            // otherwise one exposed memory round trip per warp
+            const int bn = p.worklist ? p.worklist[t + nw] : t + nw;
+            const char* nx = (const char*)(p.D + (size_t)bn * p.strideB);
+            const int bytes = ((N - 1) * p.ld + N) * 4;
+            for (int o = lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
+        }
         s.run(p, b);
         __syncwarp();
     }
