@@ -448,12 +448,17 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
     }
 
     // ------------------------------------------------------------------ radix sort of (K(), P())
-    __device__ __forceinline__ void sort_edges() {
+    // `varying`: bits in which the valid keys differ.  A byte that is the same in every key needs no
+    // pass (EEG distances share their top byte); the padding keys sit at the end and stay there
+    __device__ __forceinline__ void sort_edges(uint32_t varying) {
         uint32_t* srcK = K(); uint16_t* srcP = P();
         uint32_t* dstK = K2(); uint16_t* dstP = P2();
         const uint32_t lt = lanemask_lt();
+        int done = 0;
         for (int pass = 0; pass < 4; ++pass) {
             const int shift = 8 * pass;
+            if (!((varying >> shift) & 255u)) continue;
+            ++done;
 #pragma unroll
             for (int t = 0; t < 8; ++t) hist()[lane + 32 * t] = 0;
             __syncwarp();
@@ -492,6 +497,10 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
             uint32_t* tk = srcK; srcK = dstK; dstK = tk;
             uint16_t* tp = srcP; srcP = dstP; dstP = tp;
         }
+        if (done & 1) {  // an odd number of passes left the result in the ping-pong buffers
+            for (int k = lane; k < epad(); k += 32) { K()[k] = K2()[k]; P()[k] = P2()[k]; }
+            __syncwarp();
+        }
     }
 
     // ------------------------------------------------------------------ one window
@@ -504,6 +513,7 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
         for (int w = 0; w < W; ++w) live[w] = used[w] = 0;
         // ---- keys, initial order = descending edge index
         int valid = 0, nan_seen = 0;
+        uint32_t k_or = 0, k_and = 0xFFFFFFFFu;
         for (int k = e() + lane; k < epad(); k += 32) { K()[k] = 0xFFFFFFFFu; P()[k] = 0; }
         for (int row = 0; row < n() - 1; ++row) {
             for (int i = row + 1 + lane; i < n(); i += 32) {
@@ -511,9 +521,11 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
                 const bool ok = d <= p.thresh;
                 nan_seen |= (d != d);
                 const int k = e() - 1 - (c2(i) + row);
-                K()[k] = ok ? float_key(d) : 0xFFFFFFFFu;
+                const uint32_t key = ok ? float_key(d) : 0xFFFFFFFFu;
+                K()[k] = key;
                 P()[k] = (uint16_t)((i << 6) | row);
                 valid += ok;
+                k_or |= key; k_and &= key;
             }
         }
         for (int v = lane; v < n(); v += 32) { comp()[v] = (uint8_t)v; eld()[v] = (uint8_t)v; }
@@ -521,10 +533,13 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
         for (int o = 16; o; o >>= 1) {
             valid += __shfl_xor_sync(kFull, valid, o);
             nan_seen |= __shfl_xor_sync(kFull, nan_seen, o);
+            k_or |= __shfl_xor_sync(kFull, k_or, o);
+            k_and &= __shfl_xor_sync(kFull, k_and, o);
         }
         m = valid;
         __syncwarp();
-        sort_edges();
+        // with absent edges (d > thresh, NaN) in between, every pass runs
+        sort_edges(m < e() ? kFull : (k_or ^ k_and));
         __syncwarp();
         // ---- tie flags (the keys are about to be overwritten by the rank matrix)
         for (int k0 = 0; k0 < m; k0 += 32) {
