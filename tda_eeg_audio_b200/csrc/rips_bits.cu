@@ -367,12 +367,9 @@ template <int CPL, int NT> struct BitWarp {
 #pragma unroll
             for (int t = 0; t < 8; ++t) hist()[lane + 32 * t] = 0;
             __syncwarp();
-            for (int k0 = 0; k0 < epad(); k0 += 32) {
-                const uint32_t dg = (srcK[k0 + lane] >> shift) & 255u;
-                const uint32_t peers = __match_any_sync(kFull, dg);
-                if ((peers & lt) == 0) hist()[dg] += __popc(peers);
-                __syncwarp();
-            }
+            // digit histogram: shared-memory atomics, no ordering needed here (independent iterations)
+            for (int k0 = 0; k0 < epad(); k0 += 32) atomicAdd(hist() + ((srcK[k0 + lane] >> shift) & 255u), 1u);
+            __syncwarp();
             uint32_t loc[8], sum = 0;
 #pragma unroll
             for (int t = 0; t < 8; ++t) { loc[t] = hist()[lane * 8 + t]; sum += loc[t]; }

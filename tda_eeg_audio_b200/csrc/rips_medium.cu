@@ -454,12 +454,8 @@ template <int MW, int W> struct Cta {
 #pragma unroll
             for (int t = 0; t < 8; ++t) myh[lane + 32 * t] = 0;
             __syncwarp();
-            for (int k0 = k_begin; k0 < k_end; k0 += 32) {
-                uint32_t dg = (srcK[k0 + lane] >> shift) & 255u;
-                uint32_t peers = __match_any_sync(kFull, dg);
-                if ((peers & lt) == 0) myh[dg] += __popc(peers);
-                __syncwarp();
-            }
+            // digit histogram of this warp's segment: shared-memory atomics (independent iterations)
+            for (int k0 = k_begin; k0 < k_end; k0 += 32) atomicAdd(myh + ((srcK[k0 + lane] >> shift) & 255u), 1u);
             __syncthreads();
             if (warp == 0) {
                 // per digit: exclusive prefix over warps, then exclusive scan over digits
