@@ -291,14 +291,14 @@ def main():
     # DRAM traffic and instruction count of the same launch from the committed ncu capture
     traffic = issue = None
     try:
-        ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_rips_small_v3_bench_ncu.json")))
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_rips_small_bench_ncu.json")))
         traffic = ncu["traffic_bytes"] * B / ncu["windows"]
         sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
         slots = 148 * 4 * sm_mhz * 1e6                      # warp-instruction issue slots per second
         ips = ncu["warp_instructions_per_window"] * B / (k_avg_ms * 1e-3)
         issue = {"bound": "issue slots (148 SMs x 4 schedulers x sm clock)", "achieved": ips, "peak": slots,
                  "unit": "warp-instructions/s", "frac": ips / slots,
-                 "source": "profiles/r01_rips_small_v3_bench_ncu.json (smsp__inst_executed.sum of the same launch)"}
+                 "source": "profiles/r01_rips_small_bench_ncu.json (smsp__inst_executed.sum of the same launch)"}
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "rips_small_kernel<2,false>", "achieved": achieved, "peak": peak,
