@@ -38,7 +38,6 @@ struct Stage {
 constexpr int kStages = 3;
 Stage g_stage[kStages];
 DevBuf g_feats, g_table;
-cudaEvent_t g_done[kStages] = {nullptr, nullptr, nullptr};
 std::mutex g_mu;
 
 inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
