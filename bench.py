@@ -273,9 +273,9 @@ def main():
     for _ in range(args.steps):
         step()
     torch.cuda.synchronize()
-    k_ms, k_n = _lib.profile_query("rips_small_w2")
+    k_ms, k_n = _lib.profile_query("rips_small_w1")     # tier 1 of 47-point windows (one-word masks)
     parts = {}
-    for name in ("rips_small_w2", "rips_small_w4", "rips_small_w64", "pers_features", "aggregate_windows"):
+    for name in ("rips_small_w1", "rips_small_w2", "rips_small_w4", "rips_small_w64", "pers_features", "aggregate_windows"):
         tms, tn = _lib.profile_query(name)
         parts[name] = round(tms / max(args.steps, 1), 4)
     _lib.profile_enable(False)
@@ -301,7 +301,7 @@ def main():
                  "source": "profiles/r01_rips_small_bench_ncu.json (smsp__inst_executed.sum of the same launch)"}
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "rips_small_kernel<2,false>", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "rips_small_kernel<1,false,47>", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "issue_roofline": issue,
                 "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s",
                 "kernel_ms": k_avg_ms, "algorithmic_bytes_per_launch": alg_bytes,

@@ -25,7 +25,8 @@
 //   * tie runs (equal float32 lengths) are replayed in the exact simplexwise order (all edges of
 //     the run, then the run's triangles in descending index, apparent pairs recognised inside the
 //     run) so that the persistence PAIRS, not only the diagrams, are bit-identical to Ripser's.
-//   * capacity tiers: W=2 (64 simultaneous classes, shared memory) -> W=4 -> W=64 with PHI in a
+//   * capacity tiers: W=1 (32 simultaneous classes; 47-point windows only, where 99.95 % of the EEG
+//     windows fit) -> W=2 (64 classes, shared memory) -> W=4 -> W=64 with PHI in a
 //     global scratch; a window that exceeds a tier is pushed on a device-side list and redone by
 //     the next tier, no host round-trip.
 #include <cuda_runtime.h>
@@ -43,7 +44,7 @@ template <int W, bool PHI_GLOBAL> struct Layout {
     // all sizes in bytes, per warp
     static __host__ __device__ int epad(int N) { return (c2(N) + 31) & ~31; }
     static __host__ __device__ int ldt(int N) { return ((((N + 1) / 2) | 1) * 2); }  // u16 per T row, odd #words
-    static __host__ __device__ int recs(int N) { return PHI_GLOBAL ? c2(N) + 64 : 48 * W; }
+    static __host__ __device__ int recs(int N) { return PHI_GLOBAL ? c2(N) + 64 : (W < 2 ? 96 : 48 * W); }
     static __host__ __device__ size_t a16(size_t x) { return (x + 15) & ~(size_t)15; }
     static __host__ __device__ size_t region_a(int N) {      // sort keys + histogram | rank matrix T
         size_t s1 = (size_t)epad(N) * 4 + 1024, s2 = (size_t)N * ldt(N) * 2;
@@ -791,7 +792,7 @@ static WsLayout ws_layout(int B, int N) {
 
 template <int W, bool G, int NT>
 static cudaError_t launch_tier(const Params& p, int warps_per_block, int grid, cudaStream_t st) {
-    ProfScope prof(W == 2 ? "rips_small_w2" : (W == 4 ? "rips_small_w4" : "rips_small_w64"), st);
+    ProfScope prof(W == 1 ? "rips_small_w1" : (W == 2 ? "rips_small_w2" : (W == 4 ? "rips_small_w4" : "rips_small_w64")), st);
     size_t smem = Layout<W, G>::bytes(p.N) * warps_per_block;
     cudaError_t e = cudaFuncSetAttribute(rips_small_kernel<W, G, NT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -840,8 +841,26 @@ extern "C" int tda_rips_h01_batched(const float* D, int B, int N, int ld, long l
     const char* eng = getenv("TDA_RIPS_ENGINE");
     if (!(eng && eng[0] == 'b')) {
         // tiers 1-2: PHI per edge, lanes = apexes
-        {
+        const char* w1 = getenv("TDA_RIPS_W1");   // "0" switches the one-word tier off (A/B measurements)
+        const bool tier0 = (N == 47) && !(w1 && w1[0] == '0');
+        if (tier0) {
+            // 47-point windows rarely hold more than 32 classes at once: a one-word tier first
             p.worklist = nullptr; p.n_work = nullptr;
+            p.overflow_list = (int*)(w8 + wl.list2); p.n_overflow = counters + 2;
+            int wpb = (int)(((227 * 1024) / 2 - 1024) / Layout<1, false>::bytes(N));
+            if (wpb < 1) wpb = 1;
+            if (wpb > 8) wpb = 8;
+            size_t smem = Layout<1, false>::bytes(N) * wpb;
+            int per_sm = (int)((227 * 1024) / (smem + 1024));
+            if (per_sm < 1) per_sm = 1;
+            if (per_sm > 2) per_sm = 2;
+            long long need = ((long long)B + wpb - 1) / wpb;
+            int grid = (int)((long long)sms * per_sm < need ? (long long)sms * per_sm : need);
+            e = launch_tier<1, false, 47>(p, wpb, grid, st);
+            if (e != cudaSuccess) return (int)e;
+        }
+        {
+            p.worklist = tier0 ? (const int*)(w8 + wl.list2) : nullptr; p.n_work = tier0 ? counters + 2 : nullptr;
             p.overflow_list = (int*)(w8 + wl.list1); p.n_overflow = counters + 0;
             int wpb = (int)(((227 * 1024) / 2 - 1024) / Layout<2, false>::bytes(N));
             if (wpb < 1) wpb = 1;
@@ -850,7 +869,7 @@ extern "C" int tda_rips_h01_batched(const float* D, int B, int N, int ld, long l
             int per_sm = (int)((227 * 1024) / (smem + 1024));
             if (per_sm < 1) per_sm = 1;
             if (per_sm > 2) per_sm = 2;
-            long long need = ((long long)B + wpb - 1) / wpb;
+            long long need = tier0 ? (long long)sms * per_sm : ((long long)B + wpb - 1) / wpb;
             int grid = (int)((long long)sms * per_sm < need ? (long long)sms * per_sm : need);
             e = (N == 47) ? launch_tier<2, false, 47>(p, wpb, grid, st) : launch_tier<2, false, 0>(p, wpb, grid, st);
             if (e != cudaSuccess) return (int)e;

@@ -22,4 +22,4 @@ for cap1 in (1035, 64):
         c = out["counts"]
         print(f"B={B} cap1={cap1} pairs={want}: {ms:.3f} ms  {B/ms*1e3:.3e} diag/s  meanH1={c[:,1].float().mean().item():.2f} maxH1={c[:,1].max().item()} status_nonzero={(out['status']!=0).sum().item()}")
 ws = out["ws"][:64].view(torch.int32)
-print("tier overflow counters:", ws[:2].tolist())
+print("tier overflow counters:", ws[:3].tolist())
