@@ -47,9 +47,12 @@ template <int W, bool PHI_GLOBAL> struct Layout {
     static __host__ __device__ int recs(int N) { return PHI_GLOBAL ? c2(N) + 64 : (W < 2 ? 96 : 48 * W); }
     static __host__ __device__ size_t a16(size_t x) { return (x + 15) & ~(size_t)15; }
     static __host__ __device__ size_t region_a(int N) {      // sort keys + histogram | rank matrix T
-        size_t s1 = (size_t)epad(N) * 4 + 1024, s2 = (size_t)N * ldt(N) * 2;
+        size_t s1 = (size_t)epad(N) * 4 + 512, s2 = (size_t)N * ldt(N) * 2;   // 256 u16 digit counters
         return a16(s1 > s2 ? s1 : s2);
     }
+    // death records of the one-word tier live in a global scratch (written ~40 times per window): the
+    // kilobyte this frees lets eight warps share a CTA, sixteen an SM
+    static constexpr bool kRecGlobal = PHI_GLOBAL || W == 1;
     // sort ping-pong | PHI (phicap() ranks; all of them unless the region is made smaller)
     static __host__ __device__ size_t region_c(int N) {
         size_t s1 = (size_t)epad(N) * 6, s2 = PHI_GLOBAL ? 0 : (size_t)c2(N) * W * 4;
@@ -62,11 +65,11 @@ template <int W, bool PHI_GLOBAL> struct Layout {
     }
     static __host__ __device__ size_t off_p(int N) { return region_a(N) + region_c(N); }
     static __host__ __device__ size_t off_rec(int N) { return off_p(N) + a16((size_t)epad(N) * 2); }
-    static __host__ __device__ size_t off_visit(int N) { return off_rec(N) + (PHI_GLOBAL ? 0 : (size_t)recs(N) * 12); }
+    static __host__ __device__ size_t off_visit(int N) { return off_rec(N) + (kRecGlobal ? 0 : (size_t)recs(N) * 12); }
     static __host__ __device__ size_t bytes(int N) {
         size_t s = region_a(N) + region_c(N);
         s += a16((size_t)epad(N) * 2);                        // P
-        s += PHI_GLOBAL ? 0 : (size_t)recs(N) * 12;           // death records
+        s += kRecGlobal ? 0 : (size_t)recs(N) * 12;           // death records
         s += (size_t)epad(N) / 8;                             // visit bitmap
         s += 32 * W * 2;                                      // brank
         s += 2 * kMaxN;                                       // comp, eld
@@ -91,7 +94,7 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
     __device__ __forceinline__ int phicap() const { return L::phicap(n()); }
     // region A: sort keys + histogram, later the rank matrix T (row stride ldtv())
     __device__ __forceinline__ uint32_t* K() const { return (uint32_t*)base; }
-    __device__ __forceinline__ uint32_t* hist() const { return (uint32_t*)(base + (size_t)epad() * 4); }
+    __device__ __forceinline__ uint16_t* hist() const { return (uint16_t*)(base + (size_t)epad() * 4); }
     __device__ __forceinline__ uint16_t* T() const { return (uint16_t*)base; }
     // region C: sort ping-pong, later PHI[rank][W]
     __device__ __forceinline__ uint32_t* K2() const { return (uint32_t*)(base + L::region_a(n())); }
@@ -100,7 +103,7 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
     // P[rank] = j | i << 6 | flags
     __device__ __forceinline__ uint16_t* P() const { return (uint16_t*)(base + L::off_p(n())); }
     // death records [3][R]: birth rank, death rank, death triangle
-    __device__ __forceinline__ uint32_t* rec() const { return PHI_GLOBAL ? rec_g : (uint32_t*)(base + L::off_rec(n())); }
+    __device__ __forceinline__ uint32_t* rec() const { return L::kRecGlobal ? rec_g : (uint32_t*)(base + L::off_rec(n())); }
     __device__ __forceinline__ uint32_t* visit() const { return (uint32_t*)(base + L::off_visit(n())); }
     __device__ __forceinline__ uint16_t* brank() const { return (uint16_t*)(base + L::off_visit(n()) + (size_t)epad() / 8); }
     __device__ __forceinline__ uint8_t* comp() const { return base + L::off_visit(n()) + (size_t)epad() / 8 + 32 * W * 2; }
@@ -461,10 +464,14 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
             if (!((varying >> shift) & 255u)) continue;
             ++done;
 #pragma unroll
-            for (int t = 0; t < 8; ++t) hist()[lane + 32 * t] = 0;
+            for (int t = 0; t < 4; ++t) reinterpret_cast<uint32_t*>(hist())[lane + 32 * t] = 0;
             __syncwarp();
             // digit histogram: shared-memory atomics, no ordering needed here (independent iterations)
-            for (int k0 = 0; k0 < epad(); k0 += 32) atomicAdd(hist() + ((srcK[k0 + lane] >> shift) & 255u), 1u);
+            // (two 16-bit counters per word: counts stay below 2^16, so the halves never carry)
+            for (int k0 = 0; k0 < epad(); k0 += 32) {
+                const uint32_t dg = (srcK[k0 + lane] >> shift) & 255u;
+                atomicAdd(reinterpret_cast<uint32_t*>(hist()) + (dg >> 1), 1u << (16 * (dg & 1u)));
+            }
             __syncwarp();
             uint32_t loc[8], sum = 0;
 #pragma unroll
@@ -478,7 +485,7 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
             uint32_t run = incl - sum;
             __syncwarp();
 #pragma unroll
-            for (int t = 0; t < 8; ++t) { hist()[lane * 8 + t] = run; run += loc[t]; }
+            for (int t = 0; t < 8; ++t) { hist()[lane * 8 + t] = (uint16_t)run; run += loc[t]; }
             __syncwarp();
             for (int k0 = 0; k0 < epad(); k0 += 32) {
                 const uint32_t key = srcK[k0 + lane];
@@ -489,7 +496,7 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
                 __syncwarp();
                 dstK[pos] = key;
                 dstP[pos] = pay;
-                if ((peers & lt) == 0) hist()[dg] += __popc(peers);
+                if ((peers & lt) == 0) hist()[dg] = (uint16_t)(hist()[dg] + __popc(peers));
                 __syncwarp();
             }
             uint32_t* tk = srcK; srcK = dstK; dstK = tk;
@@ -752,7 +759,7 @@ __global__ void __launch_bounds__(256, 1) rips_small_kernel(Params p) {
     s.Nrt = N;
     s.ld = p.ld;
     s.phi_g = PHI_GLOBAL ? p.phi_global + (size_t)gw * c2(N) * W : nullptr;
-    s.rec_g = PHI_GLOBAL ? p.rec_global + (size_t)gw * 3 * L::recs(N) : nullptr;
+    s.rec_g = L::kRecGlobal ? p.rec_global + (size_t)gw * 3 * L::recs(N) : nullptr;
     s.defv_g = p.defv_global + (size_t)gw * L::epad(N);
     const int total = p.worklist ? *p.n_work : p.B;
     for (int t = gw; t < total; t += nw) {
@@ -775,7 +782,7 @@ constexpr int kLastW = 64;
 constexpr int kLastGrid = 148;   // one single-warp CTA per SM on the last tier
 constexpr int kMaxWarps = 148 * 16;  // upper bound on resident warps of any tier
 struct WsLayout {
-    size_t counters, list1, list2, defv, phi, rec, total;
+    size_t counters, list1, list2, defv, phi, rec, rec0, total;
 };
 static WsLayout ws_layout(int B, int N) {
     WsLayout w;
@@ -786,6 +793,7 @@ static WsLayout ws_layout(int B, int N) {
     w.defv = o; o += (size_t)kMaxWarps * Layout<2, false>::epad(N);
     w.phi = o; o += (size_t)kLastGrid * c2(N) * kLastW * 4;
     w.rec = o; o += (size_t)kLastGrid * 4 * Layout<kLastW, true>::recs(N) * 4;
+    w.rec0 = o; o += (size_t)kMaxWarps * 3 * Layout<1, false>::recs(N) * 4;
     w.total = o;
     return w;
 }
@@ -847,6 +855,7 @@ extern "C" int tda_rips_h01_batched(const float* D, int B, int N, int ld, long l
             // 47-point windows rarely hold more than 32 classes at once: a one-word tier first
             p.worklist = nullptr; p.n_work = nullptr;
             p.overflow_list = (int*)(w8 + wl.list2); p.n_overflow = counters + 2;
+            p.rec_global = (uint32_t*)(w8 + wl.rec0);
             int wpb = (int)(((227 * 1024) / 2 - 1024) / Layout<1, false>::bytes(N));
             if (wpb < 1) wpb = 1;
             if (wpb > 8) wpb = 8;
