@@ -18,7 +18,7 @@ import numpy as np
 
 from . import audio as _audio
 from . import dsp, pipeline, storage
-from .features import FEATURE_NAMES, diagram_features
+from .features import FEATURE_NAMES, aggregate_windows, diagram_features
 from .rips import rips_h01_batched
 
 WINDOW_SEC = 1.0
@@ -128,12 +128,13 @@ def process_file_features(file_dir, freq_bands, max_dim=1, max_edge_length=2.0, 
         if len(use) == 0:
             continue
         r = _eeg_rips(dm[use], max_edge_length)
-        f = diagram_features(r).cpu().numpy()                          # (n_used, 2, 11)
+        f = diagram_features(r)                                        # (n_used, 2, 11) on the device
+        row = aggregate_windows(f.view(1, 1, len(use), 2, 11))[0].cpu().numpy()   # 44 values, feature-major
         for k, feat in enumerate(FEATURE_NAMES):
-            file_features[f"{band}_h0_{feat}_mean"] = np.mean(f[:, 0, k])
-            file_features[f"{band}_h0_{feat}_std"] = np.std(f[:, 0, k])
-            file_features[f"{band}_h1_{feat}_mean"] = np.mean(f[:, 1, k])
-            file_features[f"{band}_h1_{feat}_std"] = np.std(f[:, 1, k])
+            file_features[f"{band}_h0_{feat}_mean"] = row[4 * k]
+            file_features[f"{band}_h0_{feat}_std"] = row[4 * k + 1]
+            file_features[f"{band}_h1_{feat}_mean"] = row[4 * k + 2]
+            file_features[f"{band}_h1_{feat}_std"] = row[4 * k + 3]
     metadata["n_windows_total"] = int(sum(metadata["n_windows"].values()))
     metadata["n_windows_used_total"] = int(sum(metadata["n_windows_used"].values()))
     return file_features, metadata
