@@ -102,3 +102,43 @@ def test_large_engine_model_matches_oracle():
         a = pcoh_large.rips_h01(D, 2.0)
         _same(rips.ripser(D, thresh=2.0, distance_matrix=True), a)
         assert a["stats"]["visited_edges"] < a["stats"]["edges"]
+
+
+def _gf2_rank(rows):
+    """rank over GF(2) of a list of python-int bit rows"""
+    rank = 0
+    rows = list(rows)
+    while rows:
+        r = rows.pop()
+        if r == 0:
+            continue
+        rank += 1
+        low = r & -r
+        rows = [x ^ r if x & low else x for x in rows]
+    return rank
+
+
+def test_oracle_against_independent_libraries_and_linear_algebra():
+    """Anchors that do not share code with the oracle: (1) the finite H0 deaths are the weights of
+    scipy's minimum spanning tree; (2) at any scale t the number of H1 bars alive is the first Betti
+    number of the Rips complex, computed from GF(2) ranks of its boundary matrices."""
+    from itertools import combinations
+    from scipy.sparse.csgraph import minimum_spanning_tree
+    rng = np.random.default_rng(5)
+    for D in list(inputs.circle_cloud(rng, 3, 14)) + list(inputs.sym_uniform(rng, 3, 12)):
+        n = len(D)
+        r = rips.ripser(D, thresh=np.inf, distance_matrix=True)
+        h0 = r["dgms"][0]
+        mst = np.sort(minimum_spanning_tree(np.triu(D.astype(np.float64), 1)).data.astype(np.float32))
+        assert np.array_equal(h0[:-1, 1].astype(np.float32), mst) and np.isinf(h0[-1, 1])
+        h1 = r["dgms"][1]
+        for t in np.quantile(D[np.triu_indices(n, 1)], [0.2, 0.4, 0.6, 0.8]).astype(np.float32):
+            edges = [(i, j) for i, j in combinations(range(n), 2) if D[i, j] <= t]
+            eid = {e: k for k, e in enumerate(edges)}
+            d1 = [(1 << i) | (1 << j) for i, j in edges]                       # rows: edges over vertices
+            d2 = [(1 << eid[(a, b)]) | (1 << eid[(a, c)]) | (1 << eid[(b, c)])
+                  for a, b, c in combinations(range(n), 3)
+                  if (a, b) in eid and (a, c) in eid and (b, c) in eid]        # rows: triangles over edges
+            betti1 = len(edges) - _gf2_rank(d1) - _gf2_rank(d2)
+            alive = int(((h1[:, 0] <= t) & (h1[:, 1] > t)).sum())
+            assert alive == betti1, (n, float(t), alive, betti1)

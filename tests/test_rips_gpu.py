@@ -159,3 +159,16 @@ def test_alternative_class_per_lane_tiers(cuda, monkeypatch):
         _compare((np.round(D * 8) / 8).astype(np.float32), np.inf)
     _compare(inputs.circle_cloud(rng, 32, 40), 0.9)
     _compare(np.ones((2, 47, 47), np.float32) - np.eye(47, dtype=np.float32), 2.0)
+
+
+def test_h0_is_the_minimum_spanning_tree(cuda):
+    """independent anchor at the EEG size: finite H0 deaths == scipy's MST weights, window by window"""
+    import torch
+    from scipy.sparse.csgraph import minimum_spanning_tree
+    from tda_eeg_audio_b200 import rips_h01_batched
+    D = inputs.eeg_like(np.random.default_rng(31), 400)
+    r = rips_h01_batched(torch.from_numpy(D).cuda(), thresh=2.0, cap1=128, want_pairs=False)
+    bd0 = r["bd0"].cpu().numpy(); cnt = r["counts"].cpu().numpy()
+    for b in range(len(D)):
+        mst = np.sort(minimum_spanning_tree(np.triu(D[b].astype(np.float64), 1)).data.astype(np.float32))
+        assert cnt[b, 0] == 47 and np.array_equal(bd0[b, :46, 1], mst) and np.isinf(bd0[b, 46, 1])

@@ -108,3 +108,33 @@ def test_large_cap1_truncation(cuda):
 def test_auto_routes_large(cuda):
     D = takens_like(np.random.default_rng(9), 2, 320)
     _compare(D, 2.0, cap1=2048, engine="auto")
+
+
+def test_full_size_properties_without_the_oracle(cuda):
+    """BASELINE configs[4] sizes (2,000 points): properties that do not need the (slow) CPU oracle.
+    (1) the finite H0 deaths are the weights of scipy's minimum spanning tree; (2) relabelling the
+    points leaves the (birth, death) multisets unchanged; (3) every bar is born before it dies and
+    births are edge lengths of the cloud."""
+    import torch
+    from scipy.sparse.csgraph import minimum_spanning_tree
+    from tda_eeg_audio_b200 import rips_h01_batched
+    n = 2000
+    D = takens_like(np.random.default_rng(42), 1, n)[0]
+    perm = np.random.default_rng(1).permutation(n)
+    Dp = D[np.ix_(perm, perm)]
+    r = rips_h01_batched(torch.from_numpy(np.stack([D, Dp])).cuda(), thresh=2.0, cap1=16384, want_pairs=False)
+    cnt = r["counts"].cpu().numpy()
+    assert (r["status"].cpu().numpy() == 0).all() and tuple(cnt[0]) == tuple(cnt[1])
+    bd0 = r["bd0"].cpu().numpy(); bd1 = r["bd1"].cpu().numpy()
+    h0 = bd0[0, :cnt[0, 0]]
+    finite = np.isfinite(h0[:, 1])
+    mst = np.sort(minimum_spanning_tree(np.triu(D.astype(np.float64), 1)).data.astype(np.float32))
+    assert np.array_equal(np.sort(h0[finite, 1]), mst[mst > 0]) and (~finite).sum() == 1
+    for dgm_a, dgm_b in ((bd0[0, :cnt[0, 0]], bd0[1, :cnt[1, 0]]), (bd1[0, :cnt[0, 1]], bd1[1, :cnt[1, 1]])):
+        a = dgm_a[np.lexsort((dgm_a[:, 1], dgm_a[:, 0]))]
+        b = dgm_b[np.lexsort((dgm_b[:, 1], dgm_b[:, 0]))]
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    h1 = bd1[0, :cnt[0, 1]]
+    assert cnt[0, 1] > 100 and (h1[:, 0] < h1[:, 1]).all()
+    lengths = np.unique(D[np.triu_indices(n, 1)])
+    assert np.isin(h1[:, 0], lengths).all() and np.isin(h1[np.isfinite(h1[:, 1]), 1], lengths).all()
