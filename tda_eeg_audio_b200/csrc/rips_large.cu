@@ -33,8 +33,8 @@
 //                     rank(e), of the visited edges the one with the LARGEST index and non-zero
 //                     coboundary mask kills its youngest class; the other classes of the mask
 //                     absorb it (PHI ^= mask wherever the dying bit is set); repeat.
-//   Capacity tiers: 256 simultaneous classes (W = 8 words; 512 above 1,024 points), then 1,024
-//   (W = 32) through a device-side hand-over list.
+//   Capacity tiers: 64 simultaneous classes first for clouds up to 256 points (W = 2 words), 256
+//   (W = 8; 512 above 1,024 points), then 1,024 (W = 32), through device-side hand-over lists.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -806,7 +806,7 @@ struct Plan {
     int N, ldT, ib, C, grid1, grid2, nth, apt, capP, capR;
     long long Emax;
     size_t cub_bytes;
-    size_t keysA, keysB, P, T, Q, defv, m, nanflag, counters, list, cub, phic1, phic2, pcr, act, rec, sglob, total;
+    size_t keysA, keysB, P, T, Q, defv, m, nanflag, counters, list, list0, cub, phic1, phic2, pcr, act, rec, sglob, total;
 };
 static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 static int bits_for(long long v) { int b = 1; while ((1ll << b) < v) ++b; return b; }
@@ -850,6 +850,7 @@ static bool make_plan(int B, int N, size_t ws_bytes, Plan& pl) {
         pl.m = o; o += al((size_t)C * 4);
         pl.nanflag = o; o += al((size_t)C * 4);
         pl.list = o; o += al((size_t)C * 4);
+        pl.list0 = o; o += al((size_t)C * 4);
         pl.keysA = o; o += al((size_t)C * pl.Emax * 8);
         pl.keysB = o; o += al((size_t)C * pl.Emax * 8);
         pl.P = o; o += al((size_t)C * pl.Emax * 4);
@@ -877,20 +878,36 @@ static bool make_plan(int B, int N, size_t ws_bytes, Plan& pl) {
     return ws_bytes == 0 || pl.total <= ws_bytes;
 }
 
-template <int NTH, int APT, int W1>
+// W0 > 0: a narrow first tier (small clouds hold few classes at once: two mask words instead of eight
+// quarter the gathers and the shared memory of a visited edge); W1: the regular first tier; then W = 32
+template <int NTH, int APT, int W0, int W1>
 static cudaError_t launch_sweeps(Params p, const Plan& pl, char* w8, cudaStream_t st) {
     int* counters = (int*)(w8 + pl.counters);
     cudaError_t e;
+    p.phic = (uint32_t*)(w8 + pl.phic1);
+    if (W0 > 0) {
+        constexpr int WN = W0 > 0 ? W0 : 2;
+        ProfScope prof("rips_large_sweep_t0", st);
+        p.worklist = nullptr; p.n_work = nullptr;
+        p.overflow_list = (int*)(w8 + pl.list0); p.n_overflow = counters + 1;
+        const size_t smem = sweep_smem<WN>(p.N, false);
+        e = cudaFuncSetAttribute(sweep_kernel<NTH, APT, WN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        const int grid = p.C < pl.grid1 ? p.C : pl.grid1;
+        sweep_kernel<NTH, APT, WN, false><<<grid, NTH, smem, st>>>(p, 0);
+        count_launch();
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
     {
         ProfScope prof("rips_large_sweep_t1", st);
-        p.worklist = nullptr; p.n_work = nullptr;
+        p.worklist = W0 > 0 ? (const int*)(w8 + pl.list0) : nullptr; p.n_work = W0 > 0 ? counters + 1 : nullptr;
         p.overflow_list = (int*)(w8 + pl.list); p.n_overflow = counters;
-        p.phic = (uint32_t*)(w8 + pl.phic1);
         const size_t smem = sweep_smem<W1>(p.N, false);
         e = cudaFuncSetAttribute(sweep_kernel<NTH, APT, W1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         const int grid = p.C < pl.grid1 ? p.C : pl.grid1;
-        sweep_kernel<NTH, APT, W1, false><<<grid, NTH, smem, st>>>(p, 0);
+        sweep_kernel<NTH, APT, W1, false><<<grid, NTH, smem, st>>>(p, W0 > 0 ? 1 : 0);
         count_launch();
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -1001,11 +1018,11 @@ extern "C" int tda_rips_h01_large(const float* D, const int* npts, int B, int N,
         }
         // 256 threads whatever the size (block barriers are what a visited edge pays for), 1-8 apexes each
         // (small clouds: one or two warps per cloud, the visited edges are issue-bound there)
-        if (N <= 128) e = launch_sweeps<32, 4, 8>(p, pl, w8, st);
-        else if (N <= 256) e = launch_sweeps<64, 4, 8>(p, pl, w8, st);
-        else if (N <= 512) e = launch_sweeps<256, 2, 8>(p, pl, w8, st);
-        else if (N <= 1024) e = launch_sweeps<256, 4, 8>(p, pl, w8, st);
-        else e = launch_sweeps<256, 8, 16>(p, pl, w8, st);
+        if (N <= 128) e = launch_sweeps<32, 4, 2, 8>(p, pl, w8, st);
+        else if (N <= 256) e = launch_sweeps<64, 4, 2, 8>(p, pl, w8, st);
+        else if (N <= 512) e = launch_sweeps<256, 2, 0, 8>(p, pl, w8, st);
+        else if (N <= 1024) e = launch_sweeps<256, 4, 0, 8>(p, pl, w8, st);
+        else e = launch_sweeps<256, 8, 0, 16>(p, pl, w8, st);
         if (e != cudaSuccess) return (int)e;
     }
     return 0;
