@@ -40,21 +40,34 @@
 namespace tda {
 namespace rips_small {
 
-template <int W, bool PHI_GLOBAL> struct Layout {
+// RSW > 0 ("register sort", RSW warps per CTA, two CTAs per SM): the keys of a radix pass travel
+// through registers, so the sort needs one key buffer and a payload ping-pong instead of two of each,
+// and the window gets a fixed budget of shared memory, 1 / (2 RSW) of an SM: [K | T] [P] [P2 + digit
+// counters | PHI] [visit, brank, comp, eld].  What is left for PHI after the other arrays sets phicap():
+// all 1,081 ranks at ten warps per CTA, 824 at eleven, 604 at twelve (a window with a class alive or
+// born beyond that rank is redone by the next tier; no EEG-like window of the benchmark is).
+template <int W, bool PHI_GLOBAL, int RSW = 0> struct Layout {
+    static constexpr bool RS = RSW > 0;
     // all sizes in bytes, per warp
     static __host__ __device__ int epad(int N) { return (c2(N) + 31) & ~31; }
     static __host__ __device__ int ldt(int N) { return ((((N + 1) / 2) | 1) * 2); }  // u16 per T row, odd #words
     static __host__ __device__ int recs(int N) { return PHI_GLOBAL ? c2(N) + 64 : (W < 2 ? 96 : 48 * W); }
     static __host__ __device__ size_t a16(size_t x) { return (x + 15) & ~(size_t)15; }
-    static __host__ __device__ size_t region_a(int N) {      // sort keys + histogram | rank matrix T
-        size_t s1 = (size_t)epad(N) * 4 + 512, s2 = (size_t)N * ldt(N) * 2;   // 256 u16 digit counters
+    static __host__ __device__ size_t region_a(int N) {      // sort keys (+ histogram) | rank matrix T
+        size_t s1 = (size_t)epad(N) * 4 + (RS ? 0 : 512), s2 = (size_t)N * ldt(N) * 2;   // 256 u16 digit counters
         return a16(s1 > s2 ? s1 : s2);
     }
     // death records of the one-word tier live in a global scratch (written ~40 times per window): the
     // kilobyte this frees lets eight warps share a CTA, sixteen an SM
     static constexpr bool kRecGlobal = PHI_GLOBAL || W == 1;
+    static __host__ __device__ size_t tail(int N) {          // visit bitmap, brank, comp, eld
+        return a16((size_t)epad(N) / 8 + 32 * W * 2 + 2 * kMaxN);
+    }
+    // an SM has 228 KB of shared memory; every resident CTA also takes 1 KB of it
+    static __host__ __device__ size_t budget() { return (size_t)(((228 * 1024) / 2 - 1024) / (RS ? RSW : 1)) & ~(size_t)15; }
     // sort ping-pong | PHI (phicap() ranks; all of them unless the region is made smaller)
     static __host__ __device__ size_t region_c(int N) {
+        if (RS) return budget() - region_a(N) - a16((size_t)epad(N) * 2) - tail(N);
         size_t s1 = (size_t)epad(N) * 6, s2 = PHI_GLOBAL ? 0 : (size_t)c2(N) * W * 4;
         return a16(s1 > s2 ? s1 : s2);
     }
@@ -63,10 +76,17 @@ template <int W, bool PHI_GLOBAL> struct Layout {
         const int cap = (int)(region_c(N) / (4 * W));
         return cap < c2(N) ? cap : c2(N);
     }
-    static __host__ __device__ size_t off_p(int N) { return region_a(N) + region_c(N); }
+    static __host__ __device__ size_t off_p(int N) { return region_a(N) + (RS ? 0 : region_c(N)); }
+    static __host__ __device__ size_t off_c(int N) { return region_a(N) + (RS ? a16((size_t)epad(N) * 2) : 0); }
+    static __host__ __device__ size_t off_hist(int N) { return RS ? off_c(N) + (size_t)epad(N) * 2 : (size_t)epad(N) * 4; }
+    static __host__ __device__ size_t off_p2(int N) { return off_c(N) + (RS ? 0 : (size_t)epad(N) * 4); }
     static __host__ __device__ size_t off_rec(int N) { return off_p(N) + a16((size_t)epad(N) * 2); }
-    static __host__ __device__ size_t off_visit(int N) { return off_rec(N) + (kRecGlobal ? 0 : (size_t)recs(N) * 12); }
+    static __host__ __device__ size_t off_visit(int N) {
+        if (RS) return budget() - tail(N);
+        return off_rec(N) + (kRecGlobal ? 0 : (size_t)recs(N) * 12);
+    }
     static __host__ __device__ size_t bytes(int N) {
+        if (RS) return budget();
         size_t s = region_a(N) + region_c(N);
         s += a16((size_t)epad(N) * 2);                        // P
         s += kRecGlobal ? 0 : (size_t)recs(N) * 12;           // death records
@@ -77,8 +97,11 @@ template <int W, bool PHI_GLOBAL> struct Layout {
     }
 };
 
-template <int W, bool PHI_GLOBAL, int NT> struct Warp {
-    typedef Layout<W, PHI_GLOBAL> L;
+// RSW (one-word 47-point tier only): see Layout
+template <int W, bool PHI_GLOBAL, int NT, int RSW = 0> struct Warp {
+    static constexpr bool kRS = RSW > 0;
+    static_assert(RSW == 0 || (NT > 0 && !PHI_GLOBAL && W == 1), "RSW variants are specialisations with a compile-time N");
+    typedef Layout<W, PHI_GLOBAL, RSW> L;
     // ---- per-warp storage: everything is an offset from `base` (compile-time when NT > 0)
     unsigned char* base;
     uint32_t* phi_g;   // PHI_GLOBAL tiers
@@ -94,12 +117,12 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
     __device__ __forceinline__ int phicap() const { return L::phicap(n()); }
     // region A: sort keys + histogram, later the rank matrix T (row stride ldtv())
     __device__ __forceinline__ uint32_t* K() const { return (uint32_t*)base; }
-    __device__ __forceinline__ uint16_t* hist() const { return (uint16_t*)(base + (size_t)epad() * 4); }
+    __device__ __forceinline__ uint16_t* hist() const { return (uint16_t*)(base + L::off_hist(n())); }
     __device__ __forceinline__ uint16_t* T() const { return (uint16_t*)base; }
     // region C: sort ping-pong, later PHI[rank][W]
-    __device__ __forceinline__ uint32_t* K2() const { return (uint32_t*)(base + L::region_a(n())); }
-    __device__ __forceinline__ uint16_t* P2() const { return (uint16_t*)(base + L::region_a(n()) + (size_t)epad() * 4); }
-    __device__ __forceinline__ uint32_t* phi() const { return PHI_GLOBAL ? phi_g : (uint32_t*)(base + L::region_a(n())); }
+    __device__ __forceinline__ uint32_t* K2() const { return (uint32_t*)(base + L::off_c(n())); }
+    __device__ __forceinline__ uint16_t* P2() const { return (uint16_t*)(base + L::off_p2(n())); }
+    __device__ __forceinline__ uint32_t* phi() const { return PHI_GLOBAL ? phi_g : (uint32_t*)(base + L::off_c(n())); }
     // P[rank] = j | i << 6 | flags
     __device__ __forceinline__ uint16_t* P() const { return (uint16_t*)(base + L::off_p(n())); }
     // death records [3][R]: birth rank, death rank, death triangle
@@ -240,7 +263,8 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
             }
             if (absorb) {
                 __syncwarp();
-                for (int q = lane; q < upto; q += 32) {
+                // (the dying cocycle vanishes on every edge older than its birth)
+                for (int q = (age & ~31) + lane; q < upto; q += 32) {
                     uint32_t* e = phi() + (size_t)q * W;
                     if (e[sw] & sb) {
 #pragma unroll
@@ -267,7 +291,7 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
         const int v1 = lane + 32;
         ed.ta[0] = 0xFFFFu; ed.tb[0] = 0xFFFFu;
         ed.ta[1] = 0xFFFFu; ed.tb[1] = 0xFFFFu;
-        if (lane < n()) { ed.ta[0] = Ti[lane]; ed.tb[0] = Tj[lane]; }
+        if (NT >= 32 || lane < n()) { ed.ta[0] = Ti[lane]; ed.tb[0] = Tj[lane]; }
         if (v1 < n()) { ed.ta[1] = Ti[v1]; ed.tb[1] = Tj[v1]; }
         return ed;
     }
@@ -285,7 +309,7 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
             return;
         }
         if (!live_any()) return;
-        if (r >= phicap()) { overflow = true; return; }
+        if (phicap() < e() && r >= phicap()) { overflow = true; return; }
         // apparent pair (e, top triangle): extend every live cocycle over e, test the other apexes
         uint32_t c[2][W];
 #pragma unroll
@@ -383,11 +407,10 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
     }
 
     __device__ __forceinline__ void tie_run(int r0, int r1) {
-        if (r1 > phicap()) {
-            // the run may touch PHI beyond this tier's capacity; only matters if a class can be alive
-            overflow = true;
-            return;
-        }
+        // a run that reaches beyond this tier's PHI capacity only matters if a class is alive in it
+        // or born in it
+        const bool beyond = r1 > phicap();
+        if (beyond && live_any()) { overflow = true; return; }
         // pass 1 (rank order): apparent pairs inside the run take no slot.  A cycle-creating run edge
         // is apparent iff its first cofacet (largest apex among the triangles present once the whole
         // run has entered) has it as youngest edge.
@@ -407,7 +430,10 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
                     const int vt = G1 ? 63 - __clz(G1) : 31 - __clz(G0);
                     if (Ti[vt] < pr && Tj[vt] < pr) dv = (uint8_t)vt;
                 }
-                if (dv == 255) birth(pr, r1);
+                if (dv == 255) {
+                    if (beyond) { overflow = true; return; }
+                    birth(pr, r1);
+                }
             }
             if (lane == 0) defv()[pr - r0] = dv;
         }
@@ -455,6 +481,68 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
     // `varying`: bits in which the valid keys differ.  A byte that is the same in every key needs no
     // pass (EEG distances share their top byte); the padding keys sit at the end and stay there
     __device__ __forceinline__ void sort_edges(uint32_t varying) {
+        if constexpr (kRS) {
+            // keys in registers (chunk t of a lane = element 32 t + lane): a pass scatters them into the
+            // one key buffer and reads them back; only the payload needs a second buffer
+            constexpr int NCH = (NT * (NT - 1) / 2 + 31) / 32;
+            uint32_t kr[NCH];
+#pragma unroll
+            for (int t = 0; t < NCH; ++t) kr[t] = K()[32 * t + lane];
+            uint16_t* srcP = P(); uint16_t* dstP = P2();
+            uint32_t* h32 = reinterpret_cast<uint32_t*>(hist());
+            const uint32_t lt = lanemask_lt();
+            int done = 0;
+            for (int pass = 0; pass < 4; ++pass) {
+                const int shift = 8 * pass;
+                if (!((varying >> shift) & 255u)) continue;
+                ++done;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) h32[lane + 32 * t] = 0;
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < NCH; ++t) {
+                    const uint32_t dg = (kr[t] >> shift) & 255u;
+                    atomicAdd(h32 + (dg >> 1), 1u << (16 * (dg & 1u)));
+                }
+                __syncwarp();
+                uint32_t loc[8], sum = 0;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) { loc[t] = hist()[lane * 8 + t]; sum += loc[t]; }
+                uint32_t incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(kFull, incl, o);
+                    if (lane >= o) incl += y;
+                }
+                uint32_t run = incl - sum;
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < 8; ++t) { hist()[lane * 8 + t] = (uint16_t)run; run += loc[t]; }
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < NCH; ++t) {
+                    const uint32_t key = kr[t];
+                    const uint16_t pay = srcP[32 * t + lane];
+                    const uint32_t dg = (key >> shift) & 255u;
+                    const uint32_t peers = __match_any_sync(kFull, dg);
+                    const uint32_t h0 = hist()[dg];
+                    const uint32_t pos = h0 + __popc(peers & lt);
+                    __syncwarp();
+                    K()[pos] = key;
+                    dstP[pos] = pay;
+                    if ((peers & lt) == 0) hist()[dg] = (uint16_t)(h0 + __popc(peers));
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int t = 0; t < NCH; ++t) kr[t] = K()[32 * t + lane];
+                uint16_t* tp = srcP; srcP = dstP; dstP = tp;
+            }
+            if (done & 1) {
+                for (int k = lane; k < epad(); k += 32) P()[k] = P2()[k];
+                __syncwarp();
+            }
+            return;
+        }
         uint32_t* srcK = K(); uint16_t* srcP = P();
         uint32_t* dstK = K2(); uint16_t* dstP = P2();
         const uint32_t lt = lanemask_lt();
@@ -533,7 +621,6 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
                 k_or |= key; k_and &= key;
             }
         }
-        for (int v = lane; v < n(); v += 32) { comp()[v] = (uint8_t)v; eld()[v] = (uint8_t)v; }
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
             valid += __shfl_xor_sync(kFull, valid, o);
@@ -546,6 +633,8 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
         // with absent edges (d > thresh, NaN) in between, every pass runs
         sort_edges(m < e() ? kFull : (k_or ^ k_and));
         __syncwarp();
+        // (after the sort: in the RSW layouts the digit counters reach into these arrays)
+        for (int v = lane; v < n(); v += 32) { comp()[v] = (uint8_t)v; eld()[v] = (uint8_t)v; }
         // ---- tie flags (the keys are about to be overwritten by the rank matrix)
         for (int k0 = 0; k0 < m; k0 += 32) {
             const int r = k0 + lane;
@@ -745,15 +834,15 @@ template <int W, bool PHI_GLOBAL, int NT> struct Warp {
     }
 };
 
-template <int W, bool PHI_GLOBAL, int NT>
-__global__ void __launch_bounds__(256, 1) rips_small_kernel(Params p) {
+template <int W, bool PHI_GLOBAL, int NT, int RSW = 0>
+__global__ void __launch_bounds__(RSW ? 32 * RSW : 256, RSW ? 2 : 1) rips_small_kernel(Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    typedef Layout<W, PHI_GLOBAL> L;
+    typedef Layout<W, PHI_GLOBAL, RSW> L;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5;
     const int gw = blockIdx.x * wpb + wib, nw = gridDim.x * wpb;
     const int N = NT > 0 ? NT : p.N;
-    Warp<W, PHI_GLOBAL, NT> s;
+    Warp<W, PHI_GLOBAL, NT, RSW> s;
     s.base = smem_raw + (size_t)wib * L::bytes(N);
     s.lane = lane;
     s.Nrt = N;
@@ -780,7 +869,7 @@ __global__ void __launch_bounds__(256, 1) rips_small_kernel(Params p) {
 // workspace layout: counters ; list1[B] ; list2[B] ; tie-run scratch ; phi scratch ; rec scratch
 constexpr int kLastW = 64;
 constexpr int kLastGrid = 148;   // one single-warp CTA per SM on the last tier
-constexpr int kMaxWarps = 148 * 16;  // upper bound on resident warps of any tier
+constexpr int kMaxWarps = 148 * 24;  // upper bound on resident warps of any tier
 struct WsLayout {
     size_t counters, list1, list2, defv, phi, rec, rec0, total;
 };
@@ -798,14 +887,17 @@ static WsLayout ws_layout(int B, int N) {
     return w;
 }
 
-template <int W, bool G, int NT>
+template <int W, bool G, int NT, int RSW = 0>
 static cudaError_t launch_tier(const Params& p, int warps_per_block, int grid, cudaStream_t st) {
     ProfScope prof(W == 1 ? "rips_small_w1" : (W == 2 ? "rips_small_w2" : (W == 4 ? "rips_small_w4" : "rips_small_w64")), st);
-    size_t smem = Layout<W, G>::bytes(p.N) * warps_per_block;
-    cudaError_t e = cudaFuncSetAttribute(rips_small_kernel<W, G, NT>,
+    size_t smem = Layout<W, G, RSW>::bytes(p.N) * warps_per_block;
+    cudaError_t e = cudaFuncSetAttribute(rips_small_kernel<W, G, NT, RSW>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    rips_small_kernel<W, G, NT><<<grid, warps_per_block * 32, smem, st>>>(p);
+    e = cudaFuncSetAttribute(rips_small_kernel<W, G, NT, RSW>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             (int)cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    rips_small_kernel<W, G, NT, RSW><<<grid, warps_per_block * 32, smem, st>>>(p);
     count_launch();
     return cudaGetLastError();
 }
@@ -856,16 +948,20 @@ extern "C" int tda_rips_h01_batched(const float* D, int B, int N, int ld, long l
             p.worklist = nullptr; p.n_work = nullptr;
             p.overflow_list = (int*)(w8 + wl.list2); p.n_overflow = counters + 2;
             p.rec_global = (uint32_t*)(w8 + wl.rec0);
-            int wpb = (int)(((227 * 1024) / 2 - 1024) / Layout<1, false>::bytes(N));
-            if (wpb < 1) wpb = 1;
-            if (wpb > 8) wpb = 8;
-            size_t smem = Layout<1, false>::bytes(N) * wpb;
-            int per_sm = (int)((227 * 1024) / (smem + 1024));
-            if (per_sm < 1) per_sm = 1;
-            if (per_sm > 2) per_sm = 2;
+            // TDA_RIPS_OPT (A/B measurements): warps per CTA of the first tier, two CTAs per SM.  8 = two
+            // sort buffers; 10, 11, 12 = register sort with a fixed budget of shared memory per window
+            const char* os = getenv("TDA_RIPS_OPT");
+            int wpb = os ? atoi(os) : 12;
+            if (wpb != 8 && wpb != 10 && wpb != 11) wpb = 12;
+            const int per_sm = 2;
             long long need = ((long long)B + wpb - 1) / wpb;
             int grid = (int)((long long)sms * per_sm < need ? (long long)sms * per_sm : need);
-            e = launch_tier<1, false, 47>(p, wpb, grid, st);
+            switch (wpb) {
+                case 8: e = launch_tier<1, false, 47, 0>(p, wpb, grid, st); break;
+                case 10: e = launch_tier<1, false, 47, 10>(p, wpb, grid, st); break;
+                case 11: e = launch_tier<1, false, 47, 11>(p, wpb, grid, st); break;
+                default: e = launch_tier<1, false, 47, 12>(p, wpb, grid, st); break;
+            }
             if (e != cudaSuccess) return (int)e;
         }
         {
