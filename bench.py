@@ -8,8 +8,9 @@ H0/H1 diagrams + persistence features + the 1416x220 feature table).
 One process per GPU (torchrun for N>1).  A step = one pass of the hot path over one batch.
 `value`   : whole-job diagrams/s with the distance matrices resident in HBM (CUDA events on the
             launch stream, barrier + synchronize on both sides, max over ranks).
-`e2e`     : the same metric through the C-ABI host entry (tda_eeg_features_host): pinned host
-            matrices in, host diagrams/features/table out, copies inside the timed region.
+`e2e`     : the same metric through the C-ABI host entry: pinned host windows in (condensed upper
+            triangles, the format of ripser's own C++ entry; the dense-matrix figure is reported
+            next to it), host diagrams/features/table out, copies inside the timed region.
 `roofline`: dominant kernel (rips_small tier 1) timed with CUDA events around its launches.
 `cpu_baseline` / --impl reference : the CPU oracle (Ripser-style C++, OpenMP over diagrams) on the
             box's host cores, on a bounded sample of the same matrices.
@@ -301,16 +302,23 @@ def main():
                  "source": "profiles/r01_rips_small_bench_ncu.json (smsp__inst_executed.sum of the same launch)"}
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "rips_small_kernel<1,false,47>", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "rips_small_kernel<1,false,47,12>", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "issue_roofline": issue,
                 "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s",
                 "kernel_ms": k_avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms_per_step": parts,
                 "note": "formally HBM-scored; the kernel is shared-memory/issue bound (see DESIGN.md)"}
 
-    # ---- e2e: pinned host buffers through the C-ABI host entry (H2D + D2H inside the timed region)
+    # ---- e2e: pinned host buffers through the C-ABI host entries (H2D + D2H inside the timed region).
+    # Headline: windows in ripser's own FFI format -- the condensed upper triangle `DParam` that
+    # ripser.py hands its C++ core (include/tda_b200.h, ld == 0), 1,081
+    # floats per window.  Also reported: the same with dense 47x47 float32 matrices (2x the bytes).
+    from tda_eeg_audio_b200.rips import condense
     h_D = torch.empty((B, N, N), dtype=torch.float32, pin_memory=True)
     h_D.copy_(D.view(B, N, N))
+    h_Dc = torch.empty((B, N * (N - 1) // 2), dtype=torch.float32, pin_memory=True)
+    for b0 in range(0, B, 65536):
+        h_Dc[b0:b0 + 65536].copy_(condense(D.view(B, N, N)[b0:b0 + 65536]))
     h_bd0 = torch.empty((B, N, 2), dtype=torch.float32, pin_memory=True)
     h_bd1 = torch.empty((B, CAP1, 2), dtype=torch.float32, pin_memory=True)
     h_cnt = torch.empty((B, 2), dtype=torch.int32, pin_memory=True)
@@ -318,39 +326,45 @@ def main():
     h_feats = torch.empty((B, 2, 11), dtype=torch.float64, pin_memory=True)
     h_table = torch.empty((R, Bd * 44), dtype=torch.float64, pin_memory=True)
     g_host = torch.empty((world * R, Bd * 44), dtype=torch.float64, pin_memory=True) if world > 1 else None
-
-    def e2e_step():
-        rc = lib.tda_eeg_features_host(h_D.data_ptr(), R, Bd, Wn, N, THRESH, CAP1, h_bd0.data_ptr(),
-                                       h_bd1.data_ptr(), h_cnt.data_ptr(), h_st.data_ptr(), h_feats.data_ptr(),
-                                       h_table.data_ptr(), local_rank)
-        if rc != 0:
-            raise RuntimeError(f"tda_eeg_features_host rc={rc}")
-        if world > 1:
-            tb = h_table.to(dev, non_blocking=True)
-            dist.all_gather_into_tensor(gathered, tb)
-            g_host.copy_(gathered, non_blocking=True)
-            torch.cuda.synchronize()
-
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / args.steps
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    h2d = h_D.numel() * 4
     d2h = (h_bd0.numel() + h_bd1.numel()) * 4 + h_cnt.numel() * 4 + h_st.numel() * 4 + \
         (h_feats.numel() + h_table.numel()) * 8
-    e2e_ok = bool(torch.equal(h_table.to(dev), res["table"]))
-    e2e = {"value": world * B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": e2e_s * 1e3, "matches_device_path": e2e_ok,
-           "h2d_gbs": h2d / e2e_s / 1e9, "note": "bound by the host->device copy of the matrices over PCIe",
-           "api": "tda_eeg_features_host (C-ABI, pinned host buffers, 3-stream chunk pipeline)"}
+
+    def measure_e2e(fn, name, h_in, layout):
+        def e2e_step():
+            rc = fn(h_in.data_ptr(), R, Bd, Wn, N, THRESH, CAP1, h_bd0.data_ptr(), h_bd1.data_ptr(),
+                    h_cnt.data_ptr(), h_st.data_ptr(), h_feats.data_ptr(), h_table.data_ptr(), local_rank)
+            if rc != 0:
+                raise RuntimeError(f"{name} rc={rc}")
+            if world > 1:
+                tb = h_table.to(dev, non_blocking=True)
+                dist.all_gather_into_tensor(gathered, tb)
+                g_host.copy_(gathered, non_blocking=True)
+                torch.cuda.synchronize()
+
+        h_table.zero_()
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        sec = (time.perf_counter() - t0) / args.steps
+        tt = torch.tensor([sec], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        sec = float(tt.item())
+        h2d = h_in.numel() * 4
+        ok = bool(torch.equal(h_table.to(dev), res["table"]))
+        return {"value": world * B / sec, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": sec * 1e3, "matches_device_path": ok, "h2d_gbs": h2d / sec / 1e9,
+                "input": layout, "api": f"{name} (C-ABI, pinned host buffers, 3-stream chunk pipeline)"}
+
+    e2e = measure_e2e(lib.tda_eeg_features_condensed_host, "tda_eeg_features_condensed_host", h_Dc,
+                      "condensed upper triangle, 1081 float32 per window (ripser's C++ entry format DParam)")
+    e2e["dense_matrices"] = measure_e2e(
+        lib.tda_eeg_features_host, "tda_eeg_features_host", h_D,
+        "dense 47x47 float32 matrices; bound by the host->device copy over PCIe")
 
     # ---- CPU baseline on a bounded sample of the same matrices (rank 0, N=1 only)
     cpu = None

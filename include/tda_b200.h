@@ -57,6 +57,11 @@ int tda_profile_query(const char* kernel, double* total_ms, int* launches);
  *
  * D       (B, N, ld) float32, item stride `strideB` elements (0 => N*ld); only D[b][i][j], i<j
  *         is read (ripser reads the upper triangle of its float32 copy).  2 <= N <= 64.
+ *         ld == 0: D is the CONDENSED form, (B, N(N-1)/2) float32 (strideB 0 => N(N-1)/2): the upper
+ *         triangle in row-major order (0,1),(0,2),...,(0,N-1),(1,2),... -- exactly the vector
+ *         `DParam` that ripser.py builds from the dense matrix and hands its C++ core
+ *         (`rips_dm(DParam, N, coeff, maxdim, thresh, ...)`), i.e. the
+ *         reference's own FFI format for this call; half the bytes of the dense form.
  * thresh  edges longer than thresh are absent; +inf => no threshold (ripser would substitute the
  *         enclosing radius, which yields the same diagrams).
  * bd0     (B, N, 2) float32  (birth, death) of H0, finite bars in ascending death order
@@ -103,6 +108,11 @@ int tda_rips_h01_large(const float* D, const int* npts, int B, int N, int ld, lo
  * streams, returns when all outputs are in host memory.  `device` is the CUDA ordinal. */
 int tda_rips_h01_host(const float* D, int B, int N, float thresh, float* bd0, long long* pr0,
                       float* bd1, long long* pr1, int* counts, int cap1, int* status, int device);
+/* The same with the condensed input of ripser's C++ entry (see `ld == 0` above): Dc (B, N(N-1)/2)
+ * float32 HOST.  The batched counterpart of ripser.py's `DRFDM(DParam, maxdim, thresh, coeff)`. */
+int tda_rips_h01_condensed_host(const float* Dc, int B, int N, float thresh, float* bd0, long long* pr0,
+                                float* bd1, long long* pr1, int* counts, int cap1, int* status,
+                                int device);
 
 /* ------------------------------------------------------------------------------------------
  * Persistence statistics / entropy features of a batch of diagrams.
@@ -231,6 +241,10 @@ int tda_wasserstein_batched(const float* bdA, const int* nA, int nA_stride, int 
 int tda_eeg_features_host(const float* D, int R, int Bd, int Wn, int N, float thresh, int cap1,
                           float* bd0, float* bd1, int* counts, int* status, double* feats,
                           double* table, int device);
+/* The same with condensed windows: Dc (R,Bd,Wn,N(N-1)/2) float32 HOST (half the PCIe bytes). */
+int tda_eeg_features_condensed_host(const float* Dc, int R, int Bd, int Wn, int N, float thresh,
+                                    int cap1, float* bd0, float* bd1, int* counts, int* status,
+                                    double* feats, double* table, int device);
 
 #ifdef __cplusplus
 }

@@ -42,6 +42,8 @@ SIGNATURES = {
     "tda_hilbert_envelope_workspace_bytes": (_sz, [_ll, _ll]),
     "tda_hilbert_envelope_f64": (_i, [_vp, _ll, _ll, _ll, _vp, _ll, _vp, _sz, _vp]),
     "tda_rips_h01_host": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i]),
+    "tda_rips_h01_condensed_host": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i]),
+    "tda_eeg_features_condensed_host": (_i, [_vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
 }
 
 _lib = None

@@ -43,11 +43,13 @@ std::mutex g_mu;
 inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // Shared body.  feats_dev != nullptr => per-window features are computed into it (B,2,11).
-int run_host(const float* D, int B, int N, float thresh, float* bd0, long long* pr0, float* bd1, long long* pr1,
-             int* counts, int cap1, int* status, double* feats_dev, double* feats_host) {
+// condensed: D holds N(N-1)/2 floats per window (upper triangle, row-major) instead of N x N.
+int run_host(const float* D, bool condensed, int B, int N, float thresh, float* bd0, long long* pr0, float* bd1,
+             long long* pr1, int* counts, int cap1, int* status, double* feats_dev, double* feats_host) {
     int chunk = 32768;
     if (chunk > B) chunk = B;
-    const size_t inB = (size_t)N * N * 4;
+    const size_t inE = condensed ? (size_t)N * (N - 1) / 2 : (size_t)N * N;   // floats per window
+    const size_t inB = inE * 4;
     const size_t o_bd0 = (size_t)N * 2 * 4, o_pr0 = (size_t)N * 2 * 8;
     const size_t o_bd1 = (size_t)cap1 * 2 * 4, o_pr1 = (size_t)cap1 * 2 * 8;
     const size_t wsB = tda_rips_h01_workspace_bytes(chunk, N);
@@ -73,9 +75,9 @@ int run_host(const float* D, int B, int N, float thresh, float* bd0, long long* 
         char* d = (char*)S.buf.dev;
         cudaStream_t st = S.stream;
         // a stage is reused only after everything queued on its stream is done (stream order)
-        e = cudaMemcpyAsync(d + f_in, D + (size_t)b0 * N * N, inB * nb, cudaMemcpyHostToDevice, st);
+        e = cudaMemcpyAsync(d + f_in, D + (size_t)b0 * inE, inB * nb, cudaMemcpyHostToDevice, st);
         if (e != cudaSuccess) { rc = (int)e; break; }
-        rc = tda_rips_h01_batched((const float*)(d + f_in), nb, N, N, 0, thresh, (float*)(d + f_bd0),
+        rc = tda_rips_h01_batched((const float*)(d + f_in), nb, N, condensed ? 0 : N, 0, thresh, (float*)(d + f_bd0),
                                   pr0 ? (long long*)(d + f_pr0) : nullptr, (float*)(d + f_bd1),
                                   pr1 ? (long long*)(d + f_pr1) : nullptr, (int*)(d + f_cnt), cap1,
                                   (int*)(d + f_st), d + f_ws, wsB, st);
@@ -111,20 +113,20 @@ int run_host(const float* D, int B, int N, float thresh, float* bd0, long long* 
 
 }  // namespace
 
-extern "C" int tda_rips_h01_host(const float* D, int B, int N, float thresh, float* bd0, long long* pr0,
-                                 float* bd1, long long* pr1, int* counts, int cap1, int* status, int device) {
+namespace {
+int rips_host(const float* D, bool condensed, int B, int N, float thresh, float* bd0, long long* pr0, float* bd1,
+              long long* pr1, int* counts, int cap1, int* status, int device) {
     if (!D || !bd0 || !bd1 || !counts || !status || B < 0 || cap1 < 0) return TDA_E_ARG;
     if (N < 2 || N > 64) return TDA_E_SIZE;
     if (B == 0) return 0;
     std::lock_guard<std::mutex> lock(g_mu);
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return (int)e;
-    return run_host(D, B, N, thresh, bd0, pr0, bd1, pr1, counts, cap1, status, nullptr, nullptr);
+    return run_host(D, condensed, B, N, thresh, bd0, pr0, bd1, pr1, counts, cap1, status, nullptr, nullptr);
 }
 
-extern "C" int tda_eeg_features_host(const float* D, int R, int Bd, int Wn, int N, float thresh, int cap1,
-                                     float* bd0, float* bd1, int* counts, int* status, double* feats,
-                                     double* table, int device) {
+int features_host(const float* D, bool condensed, int R, int Bd, int Wn, int N, float thresh, int cap1, float* bd0,
+                  float* bd1, int* counts, int* status, double* feats, double* table, int device) {
     if (!D || !table || R < 0 || Bd < 0 || Wn < 0 || cap1 < 1) return TDA_E_ARG;
     if (N < 2 || N > 64) return TDA_E_SIZE;
     const long long Bll = (long long)R * Bd * Wn;
@@ -138,7 +140,8 @@ extern "C" int tda_eeg_features_host(const float* D, int R, int Bd, int Wn, int 
     if (e != cudaSuccess) return (int)e;
     e = g_table.ensure((size_t)R * Bd * 44 * 8);
     if (e != cudaSuccess) return (int)e;
-    int rc = run_host(D, B, N, thresh, bd0, nullptr, bd1, nullptr, counts, cap1, status, (double*)g_feats.dev, feats);
+    int rc = run_host(D, condensed, B, N, thresh, bd0, nullptr, bd1, nullptr, counts, cap1, status,
+                      (double*)g_feats.dev, feats);
     if (rc != 0) return rc;
     cudaStream_t st = g_stage[0].stream;
     rc = tda_aggregate_windows((const double*)g_feats.dev, R, Bd, Wn, (double*)g_table.dev, st);
@@ -146,4 +149,28 @@ extern "C" int tda_eeg_features_host(const float* D, int R, int Bd, int Wn, int 
     e = cudaMemcpyAsync(table, g_table.dev, (size_t)R * Bd * 44 * 8, cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) return (int)e;
     return (int)cudaStreamSynchronize(st);
+}
+}  // namespace
+
+extern "C" int tda_rips_h01_host(const float* D, int B, int N, float thresh, float* bd0, long long* pr0,
+                                 float* bd1, long long* pr1, int* counts, int cap1, int* status, int device) {
+    return rips_host(D, false, B, N, thresh, bd0, pr0, bd1, pr1, counts, cap1, status, device);
+}
+
+extern "C" int tda_rips_h01_condensed_host(const float* Dc, int B, int N, float thresh, float* bd0, long long* pr0,
+                                           float* bd1, long long* pr1, int* counts, int cap1, int* status,
+                                           int device) {
+    return rips_host(Dc, true, B, N, thresh, bd0, pr0, bd1, pr1, counts, cap1, status, device);
+}
+
+extern "C" int tda_eeg_features_host(const float* D, int R, int Bd, int Wn, int N, float thresh, int cap1,
+                                     float* bd0, float* bd1, int* counts, int* status, double* feats,
+                                     double* table, int device) {
+    return features_host(D, false, R, Bd, Wn, N, thresh, cap1, bd0, bd1, counts, status, feats, table, device);
+}
+
+extern "C" int tda_eeg_features_condensed_host(const float* Dc, int R, int Bd, int Wn, int N, float thresh,
+                                               int cap1, float* bd0, float* bd1, int* counts, int* status,
+                                               double* feats, double* table, int device) {
+    return features_host(Dc, true, R, Bd, Wn, N, thresh, cap1, bd0, bd1, counts, status, feats, table, device);
 }

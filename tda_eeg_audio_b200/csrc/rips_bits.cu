@@ -99,7 +99,7 @@ template <int CPL, int NT> struct BitWarp {
     bool overflow;
 
     __device__ __forceinline__ float dist(int a, int b) const {
-        return __ldg(Db + (size_t)min(a, b) * ld + max(a, b)) + 0.0f;
+        return __ldg(Db + (d_rowoff(min(a, b), ld, n()) + max(a, b))) + 0.0f;
     }
     __device__ __forceinline__ bool live_any() const {
         uint32_t a = 0;
@@ -419,7 +419,7 @@ template <int CPL, int NT> struct BitWarp {
         for (int k = e() + lane; k < epad(); k += 32) { K()[k] = 0xFFFFFFFFu; P()[k] = 0; }
         for (int row = 0; row < n() - 1; ++row) {
             for (int i = row + 1 + lane; i < n(); i += 32) {
-                const float d = __ldg(Db + (size_t)row * ld + i) + 0.0f;
+                const float d = __ldg(Db + (d_rowoff(row, ld, n()) + i)) + 0.0f;
                 const bool ok = d <= p.thresh;
                 nan_seen |= (d != d);
                 const int k = e() - 1 - (c2(i) + row);

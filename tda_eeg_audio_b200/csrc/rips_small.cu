@@ -138,7 +138,7 @@ template <int W, bool PHI_GLOBAL, int NT, int RSW = 0> struct Warp {
     bool overflow;
 
     __device__ __forceinline__ float dist(int a, int b) const {
-        return __ldg(Db + (size_t)min(a, b) * ld + max(a, b)) + 0.0f;
+        return __ldg(Db + (d_rowoff(min(a, b), ld, n()) + max(a, b))) + 0.0f;
     }
     __device__ __forceinline__ bool live_any() const {
         uint32_t a = 0;
@@ -610,7 +610,7 @@ template <int W, bool PHI_GLOBAL, int NT, int RSW = 0> struct Warp {
         for (int k = e() + lane; k < epad(); k += 32) { K()[k] = 0xFFFFFFFFu; P()[k] = 0; }
         for (int row = 0; row < n() - 1; ++row) {
             for (int i = row + 1 + lane; i < n(); i += 32) {
-                const float d = __ldg(Db + (size_t)row * ld + i) + 0.0f;
+                const float d = __ldg(Db + (d_rowoff(row, ld, n()) + i)) + 0.0f;
                 const bool ok = d <= p.thresh;
                 nan_seen |= (d != d);
                 const int k = e() - 1 - (c2(i) + row);
@@ -858,7 +858,7 @@ __global__ void __launch_bounds__(RSW ? 32 * RSW : 256, RSW ? 2 : 1) rips_small_
             // otherwise one exposed memory round trip per warp
             const int bn = p.worklist ? p.worklist[t + nw] : t + nw;
             const char* nx = (const char*)(p.D + (size_t)bn * p.strideB);
-            const int bytes = ((N - 1) * p.ld + N) * 4;
+            const int bytes = (p.ld ? (N - 1) * p.ld + N : c2(N)) * 4;
             for (int o = lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
         }
         s.run(p, b);
@@ -916,7 +916,7 @@ extern "C" size_t tda_rips_h01_workspace_bytes(int B, int N) {
 extern "C" int tda_rips_h01_batched(const float* D, int B, int N, int ld, long long strideB, float thresh,
                                     float* bd0, long long* pr0, float* bd1, long long* pr1, int* counts,
                                     int cap1, int* status, void* ws, size_t ws_bytes, void* stream) {
-    if (!D || !bd0 || !bd1 || !counts || !status || !ws || B < 0 || cap1 < 0 || ld < N) return TDA_E_ARG;
+    if (!D || !bd0 || !bd1 || !counts || !status || !ws || B < 0 || cap1 < 0 || (ld != 0 && ld < N)) return TDA_E_ARG;
     if (N < 2 || N > kMaxN) return TDA_E_SIZE;
     if (B == 0) return 0;
     WsLayout wl = ws_layout(B, N);
@@ -927,7 +927,7 @@ extern "C" int tda_rips_h01_batched(const float* D, int B, int N, int ld, long l
     cudaError_t e = cudaMemsetAsync(counters, 0, 64, st);
     if (e != cudaSuccess) return (int)e;
     Params p;
-    p.D = D; p.strideB = strideB ? strideB : (long long)N * ld; p.ld = ld; p.N = N; p.B = B;
+    p.D = D; p.strideB = strideB ? strideB : (ld ? (long long)N * ld : (long long)c2(N)); p.ld = ld; p.N = N; p.B = B;
     p.thresh = thresh;
     p.bd0 = bd0; p.pr0 = pr0; p.bd1 = bd1; p.pr1 = pr1; p.counts = counts; p.status = status; p.cap1 = cap1;
     p.phi_global = nullptr; p.rec_global = nullptr;

@@ -42,6 +42,13 @@ struct Params {
 __host__ __device__ inline int c2(int i) { return i * (i - 1) / 2; }
 __host__ __device__ inline int c3(int i) { return i * (i - 1) * (i - 2) / 6; }
 
+// Offset of row `row` of a window's distance matrix, to which the column i > row is added.  ld >= N:
+// dense row-major matrix.  ld == 0: the condensed upper triangle in row-major order (0,1),(0,2),...,
+// (1,2),... -- the float32 vector ripser.py hands its C++ core (DParam).
+__device__ __forceinline__ long long d_rowoff(int row, int ld, int N) {
+    return ld ? (long long)row * ld : (long long)(row * (2 * N - row - 1) / 2 - row - 1);
+}
+
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));

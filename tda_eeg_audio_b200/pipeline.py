@@ -8,17 +8,23 @@ from . import features as _features
 from .rips import rips_h01_batched
 
 
-def eeg_features_from_distances(D, thresh=2.0, cap1=128, state=None, want_pairs=False):
-    """D: CUDA float32 (R, Bd, Wn, N, N).  Returns dict with
+def eeg_features_from_distances(D, thresh=2.0, cap1=128, state=None, want_pairs=False, n_points=None):
+    """D: CUDA float32 (R, Bd, Wn, N, N), or with `n_points=N` the condensed (R, Bd, Wn, N(N-1)/2)
+    of rips.condense.  Returns dict with
     table (R, Bd*44) float64, feats (R, Bd, Wn, 2, 11) float64 and the raw diagram tensors.
     `state` (a dict) keeps every buffer alive between calls so a steady-state step allocates nothing."""
     import torch
-    R, Bd, Wn, N, _ = D.shape
+    R, Bd, Wn = D.shape[:3]
     B = R * Bd * Wn
     if state is None:
         state = {}
-    rips = rips_h01_batched(D.reshape(B, N, N), thresh=thresh, cap1=cap1, want_pairs=want_pairs,
-                            out=state.setdefault("rips", {}))
+    if n_points is None:
+        N = D.shape[3]
+        rips = rips_h01_batched(D.reshape(B, N, N), thresh=thresh, cap1=cap1, want_pairs=want_pairs,
+                                out=state.setdefault("rips", {}))
+    else:
+        rips = rips_h01_batched(D.reshape(B, D.shape[3]), thresh=thresh, cap1=cap1, want_pairs=want_pairs,
+                                out=state.setdefault("rips", {}), n_points=n_points)
     feats = state.get("feats")
     if feats is None or feats.shape[0] != B:
         feats = state["feats"] = torch.empty((B, 2, 11), dtype=torch.float64, device=D.device)

@@ -16,8 +16,25 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
-def rips_h01_batched(D, thresh=float("inf"), cap1=None, want_pairs=True, out=None, npts=None, engine="auto"):
+def condense(D):
+    """(B, N, N) -> (B, N(N-1)/2): the upper triangle in row-major order, i.e. the vector `DParam`
+    that ripser.py builds (`dm[I > J]` on a meshgrid) and hands its C++ core.
+    Works on torch tensors and numpy arrays."""
+    import torch
+    n = D.shape[-1]
+    if isinstance(D, torch.Tensor):
+        iu = torch.triu_indices(n, n, 1, device=D.device)
+        return D[..., iu[0], iu[1]].contiguous()
+    iu = np.triu_indices(n, 1)
+    return np.ascontiguousarray(D[..., iu[0], iu[1]])
+
+
+def rips_h01_batched(D, thresh=float("inf"), cap1=None, want_pairs=True, out=None, npts=None, engine="auto",
+                     n_points=None):
     """D: CUDA float32 tensor (B, N, N) (any row stride; upper triangle is read), 2 <= N <= 2048.
+
+    With `n_points=N` (N <= 64), D is the condensed form (B, N(N-1)/2) of `condense` -- ripser's own
+    FFI format, half the bytes.
 
     engine="auto": N <= 64 runs the warp-per-window engine (rips_small), larger N (or ragged
     batches) the grid-cooperative engine (rips_large, 4-6x the throughput of the older
@@ -29,13 +46,26 @@ def rips_h01_batched(D, thresh=float("inf"), cap1=None, want_pairs=True, out=Non
     import torch
     _lib.require_cuda()
     lib = _lib.load()
-    if not (isinstance(D, torch.Tensor) and D.is_cuda and D.dtype == torch.float32 and D.dim() == 3):
-        raise TypeError("D must be a CUDA float32 tensor of shape (B, N, N)")
-    B, N, N2 = D.shape
-    if N != N2:
-        raise Exception("Distance matrix is not square")
-    if D.stride(2) != 1 or D.stride(1) < N:
-        D = D.contiguous()
+    condensed = n_points is not None
+    if condensed:
+        N = int(n_points)
+        if not (isinstance(D, torch.Tensor) and D.is_cuda and D.dtype == torch.float32 and D.dim() == 2
+                and D.shape[1] == N * (N - 1) // 2):
+            raise TypeError("condensed D must be a CUDA float32 tensor of shape (B, N(N-1)/2)")
+        if N > 64 or npts is not None or engine not in ("auto", "small"):
+            raise NotImplementedError("condensed input is served by the N <= 64 engine only")
+        B = D.shape[0]
+        if D.stride(1) != 1:
+            D = D.contiguous()
+        engine = "small"
+    else:
+        if not (isinstance(D, torch.Tensor) and D.is_cuda and D.dtype == torch.float32 and D.dim() == 3):
+            raise TypeError("D must be a CUDA float32 tensor of shape (B, N, N)")
+        B, N, N2 = D.shape
+        if N != N2:
+            raise Exception("Distance matrix is not square")
+        if D.stride(2) != 1 or D.stride(1) < N:
+            D = D.contiguous()
     if engine == "auto":
         engine = "small" if (N <= 64 and npts is None) else "large"
     if cap1 is None:
@@ -71,7 +101,7 @@ def rips_h01_batched(D, thresh=float("inf"), cap1=None, want_pairs=True, out=Non
         stream = torch.cuda.current_stream().cuda_stream
         if engine == "small":
             rc = lib.tda_rips_h01_batched(
-                D.data_ptr(), B, N, D.stride(1), sB, float(thresh), bd0.data_ptr(),
+                D.data_ptr(), B, N, 0 if condensed else D.stride(1), sB, float(thresh), bd0.data_ptr(),
                 _ptr(pr0), bd1.data_ptr(), _ptr(pr1), counts.data_ptr(), cap1, status.data_ptr(),
                 ws.data_ptr(), wsb, stream)
         else:

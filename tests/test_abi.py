@@ -31,6 +31,14 @@ def test_argument_errors_without_gpu():
     # null pointers / bad sizes are rejected before any CUDA call
     assert lib.tda_rips_h01_batched(None, 1, 47, 47, 0, 2.0, None, None, None, None, None, 1, None, None, 0, None) == -1
     assert lib.tda_pers_features(None, 1, None, 1, 1, None, 11, None) == -1
+    # a dense leading dimension below N is an error; 0 announces the condensed upper triangle
+    import ctypes
+    buf = (ctypes.c_char * 64)()
+    a = ctypes.addressof(buf)
+    assert lib.tda_rips_h01_batched(a, 1, 47, 46, 0, 2.0, a, None, a, None, a, 1, a, a, 0, None) == -1
+    assert lib.tda_rips_h01_batched(a, 1, 47, 0, 0, 2.0, a, None, a, None, a, 1, a, a, 0, None) == -3  # workspace too small
+    assert lib.tda_rips_h01_condensed_host(None, 1, 47, 2.0, None, None, None, None, None, 1, None, 0) == -1
+    assert lib.tda_eeg_features_condensed_host(None, 1, 5, 60, 47, 2.0, 128, None, None, None, None, None, None, 0) == -1
 
 
 def test_no_cpu_fallback():

@@ -131,6 +131,72 @@ def test_host_entry_point(cuda):
         assert np.array_equal(bd0[b], c["bd0"][b]) and np.array_equal(pr0[b], c["pr0"][b])
 
 
+@pytest.mark.parametrize("n", [2, 3, 17, 33, 47, 64])
+def test_condensed_input_equals_dense(cuda, n):
+    """ld == 0: the condensed upper triangle (ripser's own FFI vector DParam) gives bit-identical
+    outputs to the dense matrix, on every tier (uniform random matrices overflow the first ones),
+    with ties and with a binding threshold"""
+    import torch
+    from tda_eeg_audio_b200 import rips_h01_batched
+    from tda_eeg_audio_b200.rips import condense
+    rng = np.random.default_rng(100 + n)
+    U = inputs.sym_uniform(rng, 96, n)
+    cases = [(U, 2.0), (np.round(U * 16).astype(np.float32) / 16, 2.0), (U, 0.45)]
+    if n == 47:
+        cases.append((inputs.eeg_like(rng, 256), 2.0))
+    for D, th in cases:
+        Dd = torch.from_numpy(D).cuda()
+        Dc = condense(Dd)
+        assert Dc.shape == (len(D), n * (n - 1) // 2)
+        assert np.array_equal(condense(D), Dc.cpu().numpy())
+        a = rips_h01_batched(Dd, thresh=th)
+        b = rips_h01_batched(Dc, thresh=th, n_points=n)
+        torch.cuda.synchronize()
+        assert torch.equal(a["counts"], b["counts"]) and torch.equal(a["status"], b["status"])
+        cnt = a["counts"].cpu().numpy()
+        for k in ("bd0", "pr0", "bd1", "pr1"):
+            x, y = a[k].cpu().numpy(), b[k].cpu().numpy()
+            col = 0 if k.endswith("0") else 1
+            for i in range(len(D)):
+                m = min(cnt[i, col], x.shape[1])
+                assert np.array_equal(x[i, :m].view(np.uint8), y[i, :m].view(np.uint8)), (k, i)
+
+
+def test_condensed_host_entry_points(cuda):
+    """tda_rips_h01_condensed_host / tda_eeg_features_condensed_host against their dense twins"""
+    from tda_eeg_audio_b200 import _lib
+    from tda_eeg_audio_b200.rips import condense
+    lib = _lib.load()
+    R, Bd, Wn, n, cap1 = 2, 5, 6, 47, 64
+    B = R * Bd * Wn
+    D = inputs.eeg_like(np.random.default_rng(12), B)
+    Dc = condense(D)
+    outs = []
+    for fn, src in ((lib.tda_rips_h01_host, D), (lib.tda_rips_h01_condensed_host, Dc)):
+        bd0 = np.zeros((B, n, 2), np.float32); pr0 = np.zeros((B, n, 2), np.int64)
+        bd1 = np.zeros((B, cap1, 2), np.float32); pr1 = np.zeros((B, cap1, 2), np.int64)
+        counts = np.zeros((B, 2), np.int32); status = np.zeros(B, np.int32)
+        assert fn(src.ctypes.data, B, n, 2.0, bd0.ctypes.data, pr0.ctypes.data, bd1.ctypes.data,
+                  pr1.ctypes.data, counts.ctypes.data, cap1, status.ctypes.data, 0) == 0
+        outs.append((bd0, pr0, bd1, pr1, counts, status))
+    (bd0a, pr0a, bd1a, pr1a, ca, sa), (bd0b, pr0b, bd1b, pr1b, cb, sb) = outs
+    assert np.array_equal(ca, cb) and np.array_equal(sa, sb) and ca[:, 1].min() > 0
+    for i in range(B):    # rows beyond the counts are not written
+        n0, n1 = ca[i, 0], min(ca[i, 1], cap1)
+        assert np.array_equal(bd0a[i, :n0].view(np.uint8), bd0b[i, :n0].view(np.uint8))
+        assert np.array_equal(pr0a[i, :n0], pr0b[i, :n0])
+        assert np.array_equal(bd1a[i, :n1].view(np.uint8), bd1b[i, :n1].view(np.uint8))
+        assert np.array_equal(pr1a[i, :n1], pr1b[i, :n1])
+    tabs = []
+    for fn, src in ((lib.tda_eeg_features_host, D), (lib.tda_eeg_features_condensed_host, Dc)):
+        table = np.zeros((R, Bd * 44)); feats = np.zeros((B, 2, 11))
+        assert fn(src.ctypes.data, R, Bd, Wn, n, 2.0, cap1, None, None, None, None, feats.ctypes.data,
+                  table.ctypes.data, 0) == 0
+        tabs.append((table, feats))
+    assert np.array_equal(tabs[0][0], tabs[1][0]) and np.array_equal(tabs[0][1], tabs[1][1])
+    assert np.abs(tabs[0][0]).sum() > 0
+
+
 def test_ripser_shim(cuda):
     from tda_eeg_audio_b200 import ripser
     from oracle import rips
