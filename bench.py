@@ -207,6 +207,11 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback")
+    # stdout carries exactly one JSON line: whatever libraries print meanwhile (NCCL announces its
+    # version on stdout when NCCL_DEBUG is set) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -397,7 +402,10 @@ def main():
             "quality": {"mean_h1_bars": mean_h1, "h1_truncated_windows": trunc, "internal_overflow": bad},
             "secondary": secondary,
         }
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 

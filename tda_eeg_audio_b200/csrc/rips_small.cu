@@ -185,8 +185,7 @@ template <int W, bool PHI_GLOBAL, int NT, int RSW = 0> struct Warp {
         overflow = true;
         return -1;
     }
-    __device__ __forceinline__ void birth(int r, int upto) {
-        if (r >= phicap()) { overflow = true; return; }
+    __device__ __forceinline__ void birth(int r, int upto) {   // r < phicap(): see the sweep and tie_run
         const int s = alloc_slot(upto);
         if (s < 0) return;
         if (lane == 0) {
@@ -308,8 +307,8 @@ template <int W, bool PHI_GLOBAL, int NT, int RSW = 0> struct Warp {
             birth(r, r);
             return;
         }
-        if (!live_any()) return;
-        if (phicap() < e() && r >= phicap()) { overflow = true; return; }
+        // (the sweep only comes here with a class alive: with none it jumps from birth to birth, and a
+        // birth has no apex; r < phicap() is the sweep's loop bound)
         // apparent pair (e, top triangle): extend every live cocycle over e, test the other apexes
         uint32_t c[2][W];
 #pragma unroll
@@ -729,17 +728,20 @@ template <int W, bool PHI_GLOBAL, int NT, int RSW = 0> struct Warp {
         __syncwarp();
         // ---- the sweep through the live spans
         {
+            // ranks below the PHI capacity of this tier; beyond it only the question "is a class alive
+            // or born there" is left (then the window belongs to the next tier)
+            const int mlim = min(m, phicap());
+            const int nwords = epad() >> 5;
             int r = 0;
-            while (r < m && !overflow) {
+            while (r < mlim && !overflow) {
                 if (!live_any()) {
                     // jump to the next rank where a class can be born
                     int wq = r >> 5;
                     uint32_t bits = visit()[wq] & (kFull << (r & 31));
-                    const int nwords = epad() >> 5;
                     while (!bits && ++wq < nwords) bits = visit()[wq];
-                    if (!bits) break;
+                    if (!bits) { r = m; break; }
                     r = 32 * wq + __ffs(bits) - 1;
-                    if (r >= m) break;
+                    if (r >= mlim) break;
                 }
                 const uint32_t pij = P()[r];
                 if (pij & (kTie | kTiePrev)) {
@@ -753,6 +755,29 @@ template <int W, bool PHI_GLOBAL, int NT, int RSW = 0> struct Warp {
                 } else {
                     if (!(pij & kMst)) process_edge(r, fetch_edge(pij));
                     ++r;
+                }
+            }
+            if (mlim < m && !overflow && r < m) {
+                if (live_any()) overflow = true;
+                while (r < m && !overflow) {   // nothing alive: births only
+                    int wq = r >> 5;
+                    uint32_t bits = visit()[wq] & (kFull << (r & 31));
+                    while (!bits && ++wq < nwords) bits = visit()[wq];
+                    if (!bits) break;
+                    r = 32 * wq + __ffs(bits) - 1;
+                    if (r >= m) break;
+                    if (P()[r] & (kTie | kTiePrev)) {   // a tie run is visited whether or not it holds a birth
+                        int r0 = r;
+                        while (r0 > 0 && (P()[r0 - 1] & kTie)) --r0;
+                        int r1 = r;
+                        while (P()[r1] & kTie) ++r1;
+                        ++r1;
+                        tie_run(r0, r1);
+                        if (live_any()) overflow = true;
+                        r = r1;
+                    } else {
+                        overflow = true;   // a birth beyond the capacity
+                    }
                 }
             }
         }
