@@ -18,6 +18,7 @@
 // the backward pass walks the same tiles in reverse and writes only the un-padded samples.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tda_b200.h"
@@ -157,6 +158,103 @@ __global__ void __launch_bounds__(kJobs) iir_pass_kernel(const double* __restric
     }
 }
 
+// Second generation of the pass kernel (default; TDA_IIR=0 selects the first one for A/B runs): same
+// mapping and the same arithmetic, but the staging is software-pipelined.  While the CTA runs the
+// recursion on tile q out of shared memory, the sixteen values every thread contributes to tile q+1
+// are already on their way from HBM into its registers (independent, fully unrolled loads; the first
+// generation issued them one by one behind a 64-bit modulo each, and exposed the whole memory round
+// trip in front of every tile).  Row offsets are worked out once per group of jobs; two barriers per
+// tile instead of three.
+template <int FORM, bool BACKWARD>
+__global__ void __launch_bounds__(kJobs) iir_pass_kernel_v2(const double* __restrict__ in, double* __restrict__ out,
+                                                            long long n_seq, int n_bands, long long T,
+                                                            long long x_stride, int edge,
+                                                            const __grid_constant__ Coef cf) {
+    extern __shared__ __align__(16) double iir_smem[];
+    double* tin = iir_smem;
+    double* tout = iir_smem + kJobs * kLd;
+    long long* inbase = reinterpret_cast<long long*>(iir_smem + 2 * kJobs * kLd);   // element offset of a job's input row
+    long long* outbase = inbase + kJobs;                                             // ... of its output row
+    constexpr int kRows = kJobs / ((kJobs / 32) * kRPW);   // rows of a tile one thread moves (16)
+    constexpr int kRStep = (kJobs / 32) * kRPW;            // distance between them (8)
+    const long long Text = T + 2LL * edge;
+    const long long n_jobs = n_seq * n_bands;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r0 = warp * kRPW + lane / kTT;   // first tile row of this thread
+    const int c = lane % kTT;                  // its column (time within the tile)
+    const long long n_tiles = (Text + kTT - 1) / kTT;
+    for (long long job0 = (long long)blockIdx.x * kJobs; job0 < n_jobs; job0 += (long long)gridDim.x * kJobs) {
+        const long long job = job0 + tid;
+        const bool active = job < n_jobs;
+        const int band = active ? (int)(job / n_seq) : 0;
+        __syncthreads();   // the previous group's last tile has left tin / tout / the offset tables
+        inbase[tid] = active ? (BACKWARD ? job * Text : (job - (long long)band * n_seq) * x_stride) : 0;
+        outbase[tid] = active ? (BACKWARD ? job * T : job * Text) : 0;
+        State<FORM> st;
+        if (active) {
+            double scale;
+            if (!BACKWARD) scale = ext_value(in + (job - (long long)band * n_seq) * x_stride, T, edge, 0);
+            else scale = in[job * Text + (Text - 1)];
+            st.init(cf, band, scale);
+        }
+        __syncthreads();
+        const int rows_here = (int)((n_jobs - job0 < kJobs) ? (n_jobs - job0) : kJobs);
+        double nx[kRows];
+        // values of tile `tile` this thread stages: rows r0, r0 + 8, ..., column c
+        auto fetch = [&](long long tile) {
+            const long long k = tile * kTT + c;
+            const bool interior = BACKWARD || (tile * kTT >= edge && tile * kTT + kTT <= edge + T);
+#pragma unroll
+            for (int i = 0; i < kRows; ++i) {
+                const int r = r0 + kRStep * i;
+                double v = 0.0;
+                if (r < rows_here && k < Text) {
+                    const double* row = in + inbase[r];
+                    if (BACKWARD) v = row[k];
+                    else if (interior) v = row[k - edge];
+                    else v = ext_value(row, T, edge, k);
+                }
+                nx[i] = v;
+            }
+        };
+        fetch(BACKWARD ? n_tiles - 1 : 0);
+#pragma unroll
+        for (int i = 0; i < kRows; ++i) tin[(r0 + kRStep * i) * kLd + c] = nx[i];
+        __syncthreads();
+        for (long long q = 0; q < n_tiles; ++q) {
+            const long long tile = BACKWARD ? (n_tiles - 1 - q) : q;
+            const long long k0 = tile * kTT;
+            if (q + 1 < n_tiles) fetch(BACKWARD ? tile - 1 : tile + 1);   // in flight during the recursion
+            // ---- serial recursion, one job per thread
+            if (active) {
+                const int nvalid = (int)((Text - k0 < kTT) ? (Text - k0) : kTT);
+                if (!BACKWARD) {
+                    for (int cc = 0; cc < nvalid; ++cc) tout[tid * kLd + cc] = st.step(cf, band, tin[tid * kLd + cc]);
+                } else {
+                    for (int cc = nvalid - 1; cc >= 0; --cc) tout[tid * kLd + cc] = st.step(cf, band, tin[tid * kLd + cc]);
+                }
+            }
+            __syncthreads();   // tout complete, tin consumed
+            // ---- cooperative coalesced store of tile q, then the staged tile q + 1 takes tin
+            {
+                const long long k = k0 + c;
+                const bool keep = BACKWARD ? (k >= edge && k < edge + T) : (k < Text);
+                const long long ko = BACKWARD ? k - edge : k;
+#pragma unroll
+                for (int i = 0; i < kRows; ++i) {
+                    const int r = r0 + kRStep * i;
+                    if (keep && r < rows_here) out[outbase[r] + ko] = tout[r * kLd + c];
+                }
+            }
+            if (q + 1 < n_tiles) {
+#pragma unroll
+                for (int i = 0; i < kRows; ++i) tin[(r0 + kRStep * i) * kLd + c] = nx[i];
+            }
+            __syncthreads();   // tin holds tile q + 1, tout is free
+        }
+    }
+}
+
 }  // namespace iir
 }  // namespace tda
 
@@ -206,23 +304,41 @@ extern "C" int tda_filtfilt_f64(const double* x, long long n_seq, long long T, l
     if (blocks > maxb) blocks = maxb;
     cudaStream_t st = (cudaStream_t)stream;
     double* mid = (double*)ws;
-    const int smem = 2 * kJobs * kLd * (int)sizeof(double);
+    // TDA_IIR=0: first-generation kernel (A/B measurements)
+    const char* gen = getenv("TDA_IIR");
+    const bool v2 = !(gen && gen[0] == '0');
+    const int smem = 2 * kJobs * kLd * (int)sizeof(double) + (v2 ? 2 * kJobs * (int)sizeof(long long) : 0);
     cudaFuncSetAttribute(iir_pass_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(iir_pass_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(iir_pass_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(iir_pass_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(iir_pass_kernel_v2<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(iir_pass_kernel_v2<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(iir_pass_kernel_v2<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(iir_pass_kernel_v2<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int grid = (int)blocks;
     {
         tda::ProfScope prof(form == 0 ? "iir_sos_forward" : "iir_ba_forward", st);
-        if (form == 0) iir_pass_kernel<0, false><<<(int)blocks, kJobs, smem, st>>>(x, mid, n_seq, n_bands, T, x_stride, padlen, cf);
-        else iir_pass_kernel<1, false><<<(int)blocks, kJobs, smem, st>>>(x, mid, n_seq, n_bands, T, x_stride, padlen, cf);
+        if (v2) {
+            if (form == 0) iir_pass_kernel_v2<0, false><<<grid, kJobs, smem, st>>>(x, mid, n_seq, n_bands, T, x_stride, padlen, cf);
+            else iir_pass_kernel_v2<1, false><<<grid, kJobs, smem, st>>>(x, mid, n_seq, n_bands, T, x_stride, padlen, cf);
+        } else {
+            if (form == 0) iir_pass_kernel<0, false><<<grid, kJobs, smem, st>>>(x, mid, n_seq, n_bands, T, x_stride, padlen, cf);
+            else iir_pass_kernel<1, false><<<grid, kJobs, smem, st>>>(x, mid, n_seq, n_bands, T, x_stride, padlen, cf);
+        }
         tda::count_launch();
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     {
         tda::ProfScope prof(form == 0 ? "iir_sos_backward" : "iir_ba_backward", st);
-        if (form == 0) iir_pass_kernel<0, true><<<(int)blocks, kJobs, smem, st>>>(mid, y, n_seq, n_bands, T, 0, padlen, cf);
-        else iir_pass_kernel<1, true><<<(int)blocks, kJobs, smem, st>>>(mid, y, n_seq, n_bands, T, 0, padlen, cf);
+        if (v2) {
+            if (form == 0) iir_pass_kernel_v2<0, true><<<grid, kJobs, smem, st>>>(mid, y, n_seq, n_bands, T, 0, padlen, cf);
+            else iir_pass_kernel_v2<1, true><<<grid, kJobs, smem, st>>>(mid, y, n_seq, n_bands, T, 0, padlen, cf);
+        } else {
+            if (form == 0) iir_pass_kernel<0, true><<<grid, kJobs, smem, st>>>(mid, y, n_seq, n_bands, T, 0, padlen, cf);
+            else iir_pass_kernel<1, true><<<grid, kJobs, smem, st>>>(mid, y, n_seq, n_bands, T, 0, padlen, cf);
+        }
         tda::count_launch();
     }
     return (int)cudaGetLastError();
