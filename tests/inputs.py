@@ -68,3 +68,59 @@ def tiny_dataset(root, seed=5, seconds=8):
         np.save(gdir / f"{band}_correlations.npy", corr)
         np.save(gdir / f"{band}_distances.npy", dist)
     return mat, gdir
+
+
+# ------------------------------------------------------------------------------------------------
+# Known answers from theory (no code of ours, no third-party library involved)
+# ------------------------------------------------------------------------------------------------
+def cycle_metric(n, geometry="graph"):
+    """n evenly spaced points on a circle.  geometry="graph": hop distance on the n-cycle
+    (integers); "chord": Euclidean chords 2 sin(pi k / n), rounded to float32 per hop count k so
+    that equal chords are exactly equal.  By Adamaszek & Adams, "The Vietoris-Rips complexes of a
+    circle" (Pacific J. Math. 2017, Thm 7.4 / Cor. 6.7 for finite evenly spaced subsets) the Rips
+    complex at the scale of k hops is homotopy equivalent to S^1 while k/n < 1/3 and to a sphere
+    of dimension >= 2 or a wedge of 2-spheres from k/n >= 1/3 on, so H1 is ONE bar
+    [d(1 hop), d(ceil(n/3) hops)) and nothing else of non-zero persistence; H0 is n-1 bars
+    [0, d(1 hop)) and one essential class.  Returns (D float32 (n,n), birth, death)."""
+    i = np.arange(n)
+    hops = np.abs(i[:, None] - i[None, :])
+    hops = np.minimum(hops, n - hops)
+    if geometry == "graph":
+        val = np.arange(n, dtype=np.float32)
+    else:
+        val = (2.0 * np.sin(np.pi * np.arange(n) / n)).astype(np.float32)
+    D = val[hops]
+    k = -(-n // 3)
+    return D.astype(np.float32), val[1], val[k]
+
+
+def known_answer_cases():
+    """(name, D float32, thresh, expected H0 finite deaths (sorted), expected H1 bars (list of (b, d)))"""
+    s2, s3 = np.float32(np.sqrt(2.0)), np.float32(np.sqrt(3.0))
+    cases = []
+    # unit square: the 4-cycle closes at 1 and is filled by the diagonals at sqrt 2
+    sq = np.array([[0, 1, s2, 1], [1, 0, 1, s2], [s2, 1, 0, 1], [1, s2, 1, 0]], np.float32)
+    cases.append(("square", sq, np.inf, [1, 1, 1], [(np.float32(1), s2)]))
+    # the same below the diagonals: the cycle never dies
+    cases.append(("square_thresh", sq, 1.2, [1, 1, 1], [(np.float32(1), np.float32(np.inf))]))
+    # two unit squares 10 apart: two independent cycles; H0 joins the squares at distance 10, where the
+    # two facing sides and the two gaps also close a 10 x 1 rectangle, filled by its diagonal sqrt 101
+    pts = np.array([[0, 0], [1, 0], [1, 1], [0, 1], [11, 0], [12, 0], [12, 1], [11, 1]], float)
+    d2 = np.sqrt(((pts[:, None] - pts[None]) ** 2).sum(-1)).astype(np.float32)
+    cases.append(("two_squares", d2, np.inf, [1] * 6 + [10], [(np.float32(1), s2), (np.float32(1), s2),
+                                                          (np.float32(10), np.float32(np.sqrt(101.0)))]))
+    # points on a line: a tree at every scale, no H1
+    line = np.abs(np.arange(9)[:, None] - np.arange(9)[None]).astype(np.float32)
+    cases.append(("line", line, np.inf, [1] * 8, []))
+    # octahedron (6 points, antipodes at 2, all others at sqrt 2): its Rips complex at sqrt 2 is the
+    # 2-sphere, simply connected
+    octa = np.full((6, 6), s2, np.float32)
+    for a in range(3):
+        octa[2 * a, 2 * a + 1] = octa[2 * a + 1, 2 * a] = 2
+    np.fill_diagonal(octa, 0)
+    cases.append(("octahedron", octa, np.inf, [s2] * 5, []))
+    # regular hexagon with unit side: filled by the short diagonals sqrt 3 (the octahedron again)
+    D, b, d = cycle_metric(6, "chord")
+    assert b == np.float32(1) and d == s3
+    cases.append(("hexagon", D, np.inf, [1] * 5, [(b, d)]))
+    return cases

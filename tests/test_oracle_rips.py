@@ -142,3 +142,35 @@ def test_oracle_against_independent_libraries_and_linear_algebra():
             betti1 = len(edges) - _gf2_rank(d1) - _gf2_rank(d2)
             alive = int(((h1[:, 0] <= t) & (h1[:, 1] > t)).sum())
             assert alive == betti1, (n, float(t), alive, betti1)
+
+
+def _h1_multiset(dg):
+    return sorted((np.float32(b), np.float32(d)) for b, d in dg)
+
+
+def test_known_answers_from_theory():
+    """Inputs whose diagrams follow from a proof, not from any implementation: small polytopes and
+    evenly spaced points on a circle (Adamaszek-Adams).  Both CPU statements of the algorithm."""
+    from oracle import rips_naive
+    for name, D, thr, h0, h1 in inputs.known_answer_cases():
+        for impl in (lambda M, t: rips.ripser(M, thresh=t, distance_matrix=True),
+                     lambda M, t: rips_naive.rips_h01_naive(M, t)):
+            r = impl(D, thr)
+            d0 = r["dgms"][0]
+            assert np.array_equal(np.sort(d0[np.isfinite(d0[:, 1]), 1]).astype(np.float32), np.array(h0, np.float32)), name
+            assert np.isinf(d0[:, 1]).sum() == 1 and (d0[:, 0] == 0).all(), name
+            assert _h1_multiset(r["dgms"][1]) == sorted(h1), name
+
+
+@pytest.mark.parametrize("geometry", ["graph", "chord"])
+@pytest.mark.parametrize("n", [5, 6, 7, 9, 12, 16, 31, 47, 64, 100])
+def test_circle_points_known_answer(n, geometry):
+    """H1 of n evenly spaced points on a circle is exactly one bar [1 hop, ceil(n/3) hops)."""
+    D, b, d = inputs.cycle_metric(n, geometry)
+    r = rips.ripser(D, thresh=np.inf, distance_matrix=True)
+    d0, d1 = r["dgms"]
+    assert d0.shape == (n, 2) and (d0[:-1, 1] == b).all() and np.isinf(d0[-1, 1])
+    assert d1.shape == (1, 2) and np.float32(d1[0, 0]) == b and np.float32(d1[0, 1]) == d
+    if n <= 16:
+        a = rips_naive.rips_h01_naive(D, np.inf)
+        assert np.array_equal(a["dgms"][1], d1) and np.array_equal(a["pairs"][1], r["pairs"][1])

@@ -238,3 +238,38 @@ def test_h0_is_the_minimum_spanning_tree(cuda):
     for b in range(len(D)):
         mst = np.sort(minimum_spanning_tree(np.triu(D[b].astype(np.float64), 1)).data.astype(np.float32))
         assert cnt[b, 0] == 47 and np.array_equal(bd0[b, :46, 1], mst) and np.isinf(bd0[b, 46, 1])
+
+
+def test_known_answers_from_theory(cuda):
+    """Diagrams that follow from a proof (tests/inputs.py: small polytopes; evenly spaced points on
+    a circle, Adamaszek-Adams): the engines against the theory directly, no oracle in between.
+    Every engine that accepts the size; dense and condensed input."""
+    import torch
+    from tda_eeg_audio_b200 import rips_h01_batched
+    from tda_eeg_audio_b200.rips import condense
+
+    def check(name, D, thr, h0, h1, **kw):
+        r = rips_h01_batched(D, thresh=float(thr), **kw)
+        torch.cuda.synchronize()
+        n0, n1 = (int(v) for v in r["counts"][0].tolist())
+        assert int(r["status"][0]) == 0, name
+        d0 = r["bd0"][0, :n0].cpu().numpy()
+        d1 = r["bd1"][0, :n1].cpu().numpy()
+        fin = np.isfinite(d0[:, 1])
+        assert np.array_equal(np.sort(d0[fin, 1]), np.array(h0, np.float32)) and (~fin).sum() == 1 and (d0[:, 0] == 0).all(), name
+        assert sorted(map(tuple, d1)) == sorted(h1), (name, d1)
+
+    cases = inputs.known_answer_cases()
+    for n in (5, 6, 7, 9, 12, 16, 31, 33, 47, 64, 100, 250):
+        for geo in ("graph", "chord"):
+            D, b, d = inputs.cycle_metric(n, geo)
+            cases.append((f"circle{n}{geo}", D, np.inf, [b] * (n - 1), [(b, d)]))
+    for name, D, thr, h0, h1 in cases:
+        n = D.shape[0]
+        Dg = torch.from_numpy(D).cuda()[None]
+        if n <= 64:
+            check(name, Dg, thr, h0, h1)
+            check(name + "/condensed", condense(Dg), thr, h0, h1, n_points=n)
+        if n <= 254:
+            check(name + "/medium", Dg, thr, h0, h1, engine="medium")
+        check(name + "/large", Dg, thr, h0, h1, engine="large")
