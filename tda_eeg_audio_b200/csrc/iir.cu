@@ -84,6 +84,36 @@ template <int FORM> struct State {
     }
 };
 
+// The same two recursions with the band's coefficients in registers (cr = Coef::c[band]).
+template <int FORM>
+__device__ __forceinline__ double step_regs(double (&z)[8], const double (&cr)[kMaxSec * 6], int n, double x) {
+    if (FORM == 0) {
+#pragma unroll
+        for (int s = 0; s < kMaxSec; ++s) {
+            if (s < n) {
+                const double xn = __dadd_rn(__dmul_rn(cr[s * 6 + 0], x), z[2 * s]);
+                z[2 * s] = __dadd_rn(__dsub_rn(__dmul_rn(cr[s * 6 + 1], x), __dmul_rn(cr[s * 6 + 4], xn)), z[2 * s + 1]);
+                z[2 * s + 1] = __dsub_rn(__dmul_rn(cr[s * 6 + 2], x), __dmul_rn(cr[s * 6 + 5], xn));
+                x = xn;
+            }
+        }
+        return x;
+    } else {
+        if (n == 1) return __dmul_rn(x, cr[0]);
+        const double y = __dadd_rn(z[0], __dmul_rn(cr[0], x));
+#pragma unroll
+        for (int k = 0; k < kMaxTaps - 2; ++k) {
+            if (k < n - 2)
+                z[k] = __dsub_rn(__dadd_rn(z[k + 1], __dmul_rn(x, cr[k + 1])), __dmul_rn(y, cr[kMaxTaps + k + 1]));
+        }
+#pragma unroll
+        for (int k = 0; k < kMaxTaps - 1; ++k) {
+            if (k == n - 2) z[k] = __dsub_rn(__dmul_rn(x, cr[k + 1]), __dmul_rn(y, cr[kMaxTaps + k + 1]));
+        }
+        return y;
+    }
+}
+
 // value of the odd-extended signal at padded position k (scipy _arraytools.odd_ext)
 __device__ __forceinline__ double ext_value(const double* __restrict__ x, long long T, int edge, long long k) {
     if (k < edge) return __dsub_rn(__dmul_rn(2.0, x[0]), x[edge - k]);
@@ -255,6 +285,127 @@ __global__ void __launch_bounds__(kJobs) iir_pass_kernel_v2(const double* __rest
     }
 }
 
+// Third generation, STAGED: opt-in with TDA_IIR=3, compiled but not yet run on a GPU (the round's
+// GPU budget was spent), so it is neither the default nor covered by a parity run.  The second
+// generation with two changes: every group of 128 jobs belongs to ONE band, and that band's
+// coefficients are pinned in registers for the whole group instead of being fetched from the
+// constant bank at every use (20 loads next to the 36 FP64 operations of a sample in the sos form);
+// 4 CTAs per SM instead of 6.  tools/ab_iir.py measures it against the other two and compares bits.
+template <int FORM, bool BACKWARD>
+__global__ void __launch_bounds__(kJobs, 4) iir_pass_kernel_v3(const double* __restrict__ in, double* __restrict__ out,
+                                                            long long n_seq, int n_bands, long long T,
+                                                            long long x_stride, int edge,
+                                                            const __grid_constant__ Coef cf) {
+    extern __shared__ __align__(16) double iir_smem[];
+    double* tin = iir_smem;
+    double* tout = iir_smem + kJobs * kLd;
+    long long* inbase = reinterpret_cast<long long*>(iir_smem + 2 * kJobs * kLd);   // element offset of a job's input row
+    long long* outbase = inbase + kJobs;                                             // ... of its output row
+    constexpr int kRows = kJobs / ((kJobs / 32) * kRPW);   // rows of a tile one thread moves (16)
+    constexpr int kRStep = (kJobs / 32) * kRPW;            // distance between them (8)
+    const long long Text = T + 2LL * edge;
+    const long long n_jobs = n_seq * n_bands;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r0 = warp * kRPW + lane / kTT;   // first tile row of this thread
+    const int c = lane % kTT;                  // its column (time within the tile)
+    const long long n_tiles = (Text + kTT - 1) / kTT;
+    // job groups: RC -> ceil(n_seq / 128) groups per band, each within one band; else consecutive jobs
+    const long long gpb = (n_seq + kJobs - 1) / kJobs;
+    constexpr bool RC = true;
+    const long long n_groups = RC ? gpb * n_bands : (n_jobs + kJobs - 1) / kJobs;
+    for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const int gband = RC ? (int)(grp / gpb) : 0;                                  // uniform in the CTA
+        const long long seq0 = RC ? (grp - (long long)gband * gpb) * kJobs : 0;
+        const long long job0 = RC ? (long long)gband * n_seq + seq0 : grp * kJobs;
+        const long long job = job0 + tid;
+        const bool active = RC ? (seq0 + tid < n_seq) : (job < n_jobs);
+        const int band = RC ? gband : (active ? (int)(job / n_seq) : 0);
+        double cr[kMaxSec * 6];
+        if (RC) {
+#pragma unroll
+            for (int k = 0; k < kMaxSec * 6; ++k) {
+                const bool used = FORM == 0 ? (k % 6 != 3) : (k < 2 * kMaxTaps);
+                cr[k] = used ? cf.c[band][k] : 0.0;
+                if (used) asm volatile("" : "+d"(cr[k]));   // a register, not a constant-bank operand
+            }
+        }
+        __syncthreads();   // the previous group's last tile has left tin / tout / the offset tables
+        inbase[tid] = active ? (BACKWARD ? job * Text : (job - (long long)band * n_seq) * x_stride) : 0;
+        outbase[tid] = active ? (BACKWARD ? job * T : job * Text) : 0;
+        State<FORM> st;
+        if (active) {
+            double scale;
+            if (!BACKWARD) scale = ext_value(in + (job - (long long)band * n_seq) * x_stride, T, edge, 0);
+            else scale = in[job * Text + (Text - 1)];
+            st.init(cf, band, scale);
+        }
+        __syncthreads();
+        const long long left = RC ? n_seq - seq0 : n_jobs - job0;
+        const int rows_here = (int)(left < kJobs ? left : kJobs);
+        double nx[kRows];
+        // values of tile `tile` this thread stages: rows r0, r0 + 8, ..., column c
+        auto fetch = [&](long long tile) {
+            const long long k = tile * kTT + c;
+            const bool interior = BACKWARD || (tile * kTT >= edge && tile * kTT + kTT <= edge + T);
+#pragma unroll
+            for (int i = 0; i < kRows; ++i) {
+                const int r = r0 + kRStep * i;
+                double v = 0.0;
+                if (r < rows_here && k < Text) {
+                    const double* row = in + inbase[r];
+                    if (BACKWARD) v = row[k];
+                    else if (interior) v = row[k - edge];
+                    else v = ext_value(row, T, edge, k);
+                }
+                nx[i] = v;
+            }
+        };
+        fetch(BACKWARD ? n_tiles - 1 : 0);
+#pragma unroll
+        for (int i = 0; i < kRows; ++i) tin[(r0 + kRStep * i) * kLd + c] = nx[i];
+        __syncthreads();
+        for (long long q = 0; q < n_tiles; ++q) {
+            const long long tile = BACKWARD ? (n_tiles - 1 - q) : q;
+            const long long k0 = tile * kTT;
+            if (q + 1 < n_tiles) fetch(BACKWARD ? tile - 1 : tile + 1);   // in flight during the recursion
+            // ---- serial recursion, one job per thread
+            if (active) {
+                const int nvalid = (int)((Text - k0 < kTT) ? (Text - k0) : kTT);
+                if (RC) {
+                    if (!BACKWARD) {
+                        for (int cc = 0; cc < nvalid; ++cc)
+                            tout[tid * kLd + cc] = step_regs<FORM>(st.z, cr, cf.n, tin[tid * kLd + cc]);
+                    } else {
+                        for (int cc = nvalid - 1; cc >= 0; --cc)
+                            tout[tid * kLd + cc] = step_regs<FORM>(st.z, cr, cf.n, tin[tid * kLd + cc]);
+                    }
+                } else if (!BACKWARD) {
+                    for (int cc = 0; cc < nvalid; ++cc) tout[tid * kLd + cc] = st.step(cf, band, tin[tid * kLd + cc]);
+                } else {
+                    for (int cc = nvalid - 1; cc >= 0; --cc) tout[tid * kLd + cc] = st.step(cf, band, tin[tid * kLd + cc]);
+                }
+            }
+            __syncthreads();   // tout complete, tin consumed
+            // ---- cooperative coalesced store of tile q, then the staged tile q + 1 takes tin
+            {
+                const long long k = k0 + c;
+                const bool keep = BACKWARD ? (k >= edge && k < edge + T) : (k < Text);
+                const long long ko = BACKWARD ? k - edge : k;
+#pragma unroll
+                for (int i = 0; i < kRows; ++i) {
+                    const int r = r0 + kRStep * i;
+                    if (keep && r < rows_here) out[outbase[r] + ko] = tout[r * kLd + c];
+                }
+            }
+            if (q + 1 < n_tiles) {
+#pragma unroll
+                for (int i = 0; i < kRows; ++i) tin[(r0 + kRStep * i) * kLd + c] = nx[i];
+            }
+            __syncthreads();   // tin holds tile q + 1, tout is free
+        }
+    }
+}
+
 }  // namespace iir
 }  // namespace tda
 
@@ -307,6 +458,11 @@ extern "C" int tda_filtfilt_f64(const double* x, long long n_seq, long long T, l
     // TDA_IIR=0: first-generation kernel (A/B measurements)
     const char* gen = getenv("TDA_IIR");
     const bool v2 = !(gen && gen[0] == '0');
+    const bool v3 = gen && gen[0] == '3';   // staged third generation (register coefficients), opt-in
+    if (v3) {
+        const long long groups = ((n_seq + kJobs - 1) / kJobs) * n_bands;
+        blocks = groups < (long long)sms * 4 ? groups : (long long)sms * 4;
+    }
     const int smem = 2 * kJobs * kLd * (int)sizeof(double) + (v2 ? 2 * kJobs * (int)sizeof(long long) : 0);
     cudaFuncSetAttribute(iir_pass_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(iir_pass_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -316,10 +472,17 @@ extern "C" int tda_filtfilt_f64(const double* x, long long n_seq, long long T, l
     cudaFuncSetAttribute(iir_pass_kernel_v2<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(iir_pass_kernel_v2<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(iir_pass_kernel_v2<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(iir_pass_kernel_v3<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(iir_pass_kernel_v3<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(iir_pass_kernel_v3<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(iir_pass_kernel_v3<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     const int grid = (int)blocks;
     {
         tda::ProfScope prof(form == 0 ? "iir_sos_forward" : "iir_ba_forward", st);
-        if (v2) {
+        if (v3) {
+            if (form == 0) iir_pass_kernel_v3<0, false><<<grid, kJobs, smem, st>>>(x, mid, n_seq, n_bands, T, x_stride, padlen, cf);
+            else iir_pass_kernel_v3<1, false><<<grid, kJobs, smem, st>>>(x, mid, n_seq, n_bands, T, x_stride, padlen, cf);
+        } else if (v2) {
             if (form == 0) iir_pass_kernel_v2<0, false><<<grid, kJobs, smem, st>>>(x, mid, n_seq, n_bands, T, x_stride, padlen, cf);
             else iir_pass_kernel_v2<1, false><<<grid, kJobs, smem, st>>>(x, mid, n_seq, n_bands, T, x_stride, padlen, cf);
         } else {
@@ -332,7 +495,10 @@ extern "C" int tda_filtfilt_f64(const double* x, long long n_seq, long long T, l
     if (e != cudaSuccess) return (int)e;
     {
         tda::ProfScope prof(form == 0 ? "iir_sos_backward" : "iir_ba_backward", st);
-        if (v2) {
+        if (v3) {
+            if (form == 0) iir_pass_kernel_v3<0, true><<<grid, kJobs, smem, st>>>(mid, y, n_seq, n_bands, T, 0, padlen, cf);
+            else iir_pass_kernel_v3<1, true><<<grid, kJobs, smem, st>>>(mid, y, n_seq, n_bands, T, 0, padlen, cf);
+        } else if (v2) {
             if (form == 0) iir_pass_kernel_v2<0, true><<<grid, kJobs, smem, st>>>(mid, y, n_seq, n_bands, T, 0, padlen, cf);
             else iir_pass_kernel_v2<1, true><<<grid, kJobs, smem, st>>>(mid, y, n_seq, n_bands, T, 0, padlen, cf);
         } else {
