@@ -7,11 +7,14 @@
 // B200-first design (not a port of Ripser's heap-based column reduction):
 //   * one WARP owns one window; a CTA is a bundle of independent warps, the grid is sized in
 //     multiples of the SM count and every warp strides over the batch.  All state of a window
-//     lives in that warp's ~18 KB slice of shared memory — the distance matrix is read from HBM
-//     exactly once, coalesced by rows, and the diagrams are written exactly once.
-//   * filtration = per-warp stable LSD radix sort (4 x 8 bit, __match_any_sync ranking) of the
-//     order-preserving integer image of the float32 edge lengths; initial order is descending
-//     edge index so stability gives Ripser's tie-break (equal length => larger index first).
+//     lives in that warp's slice of shared memory (9.4 KB on the 47-point tier, 24 warps per SM) —
+//     the distance matrix (dense, or the condensed upper triangle ripser's own C++ entry takes) is
+//     read from HBM exactly once, coalesced by rows, and the diagrams are written exactly once.
+//   * filtration = per-warp stable LSD radix sort (8-bit digits, __match_any_sync ranking, passes over
+//     bytes shared by all keys skipped) of the order-preserving integer image of the float32 edge
+//     lengths; initial order is descending edge index so stability gives Ripser's tie-break (equal
+//     length => larger index first).  On the 47-point tier the keys of a pass travel through
+//     registers, which is what makes the window fit 9.4 KB (see Layout).
 //   * H0 = Kruskal over the sorted edges, 32 edges checked per step, warp-parallel relabelling.
 //   * the sorted ranks are scattered into a rank matrix T[i][v] (u16).  "Apex v closes a triangle
 //     over edge (i,j) of rank r" is then max(T[i][v], T[j][v]) < r: no adjacency to maintain, and
@@ -25,10 +28,10 @@
 //   * tie runs (equal float32 lengths) are replayed in the exact simplexwise order (all edges of
 //     the run, then the run's triangles in descending index, apparent pairs recognised inside the
 //     run) so that the persistence PAIRS, not only the diagrams, are bit-identical to Ripser's.
-//   * capacity tiers: W=1 (32 simultaneous classes; 47-point windows only, where 99.95 % of the EEG
-//     windows fit) -> W=2 (64 classes, shared memory) -> W=4 -> W=64 with PHI in a
-//     global scratch; a window that exceeds a tier is pushed on a device-side list and redone by
-//     the next tier, no host round-trip.
+//   * capacity tiers: W=1 (32 simultaneous classes, PHI for the first 604 ranks; 47-point windows
+//     only, where 99.95 % of the EEG windows fit) -> W=2 (64 classes, shared memory) -> W=4 ->
+//     W=64 with PHI in a global scratch; a window that exceeds a tier is pushed on a device-side
+//     list and redone by the next tier, no host round-trip.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
