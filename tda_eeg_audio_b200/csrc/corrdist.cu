@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tda_b200.h"
@@ -122,6 +123,10 @@ __global__ void __launch_bounds__(kThreads) corrdist_kernel(const double* __rest
     }
 }
 
+// corrdist_mma.cu: staged second generation (Gram on the FP64 tensor pipe), opt-in TDA_CORRDIST=mma
+int launch_corrdist_mma(const double* x, int R, int C, long long T, long long strideR, int win, int step, long long W,
+                        int method, float* D, double* corr, long long strideO, cudaStream_t stream);
+
 static size_t smem_bytes(int C, int win) {
     const int Cp = (C + kTile - 1) / kTile * kTile;
     return ((size_t)Cp * (win | 1) + (size_t)Cp * Cp + Cp) * sizeof(double);
@@ -141,6 +146,14 @@ extern "C" int tda_corrdist_windows(const double* x, int R, int C, long long T, 
     if (smem > 227 * 1024) return TDA_E_SIZE;
     if (strideR == 0) strideR = (long long)C * T;
     if (strideO == 0) strideO = W * (long long)C * C;
+    {
+        const char* gen = getenv("TDA_CORRDIST");
+        if (gen && gen[0] == 'm') {
+            const int rc = launch_corrdist_mma(x, R, C, T, strideR, win, step, W, method, D, corr, strideO,
+                                               (cudaStream_t)stream);
+            if (rc != TDA_E_SIZE) return rc;   // shapes it does not take fall through to the first generation
+        }
+    }
     cudaError_t e = cudaFuncSetAttribute(corrdist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148;
