@@ -178,7 +178,56 @@ def secondary_workloads(dev):
                      "status_nonzero": int((buf["status"] != 0).sum())}
         del D, buf
         torch.cuda.empty_cache()
+    try:
+        out["raw_eeg_to_features_256rec"] = raw_eeg_workload(dev)
+    except Exception as exc:  # a side measurement must not cost the others
+        out["raw_eeg_to_features_256rec"] = {"error": repr(exc)}
     return out
+
+
+def raw_eeg_workload(dev, R=256):
+    """SURVEY.md §8(d) config (b) "end-to-end from raw EEG", on a chunk of 256 recordings: raw
+    47-channel EEG (R, 47, 15000) float64, device-resident -> zero-phase band-pass into 5 bands ->
+    60 windows -> correlation distances -> Rips H0+H1 -> features -> (R, 220) table.  CUDA events,
+    per-stage times from the library's own event timers."""
+    import torch
+    from tda_eeg_audio_b200 import _lib, dsp, pipeline
+    g = torch.Generator(device=dev)
+    g.manual_seed(20261018)
+    A = torch.randn((R, N_CH, 8), generator=g, device=dev, dtype=torch.float64) / 8 ** 0.5
+    x = A @ torch.randn((R, 8, 15000), generator=g, device=dev, dtype=torch.float64)
+    x += 0.5 * torch.randn((R, N_CH, 15000), generator=g, device=dev, dtype=torch.float64)
+    del A
+    D = torch.empty((R, N_BANDS, N_WIN, N_CH, N_CH), dtype=torch.float32, device=dev)
+    st = {}
+
+    def run():
+        dsp.eeg_distances_from_raw(x, overlap=0.0, rec_chunk=R, out=D)
+        return pipeline.eeg_features_from_distances(D, thresh=THRESH, cap1=CAP1, state=st)
+
+    run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    _lib.profile_enable(True)
+    run()
+    torch.cuda.synchronize()
+    stages = {}
+    for name in ("iir_sos_forward", "iir_sos_backward", "corrdist", "rips_small_w1", "pers_features"):
+        tms, _ = _lib.profile_query(name)
+        stages[name] = round(tms, 3)
+    _lib.profile_enable(False)
+    res = {"recordings": R, "ms": round(ms, 3), "recordings_per_s": round(R / ms * 1e3, 1),
+           "diagrams_per_s": round(R * N_BANDS * N_WIN / ms * 1e3, 1), "stage_ms": stages,
+           "input_bytes": x.numel() * 8}
+    del x, D, st
+    torch.cuda.empty_cache()
+    return res
 
 
 def workload_config(args, world):
