@@ -72,3 +72,21 @@ def test_argument_errors_of_the_cloud_and_audio_entry_points():
     assert lib.tda_hilbert_envelope_workspace_bytes(2, 15000) >= 2 * 15000 * 16
     assert lib.tda_hilbert_envelope_f64(None, 1, 10, 10, None, 10, None, 0, None) == -1
     assert lib.tda_filtfilt_f64(None, 1, 100, 100, 0, 1, 4, None, None, 27, None, None, 0, None) == -1
+
+
+def test_condensed_order_is_ripser_py_own_expression():
+    """rips.condense must produce exactly the vector ripser.py hands its C++ core for a dense matrix:
+    `I, J = np.meshgrid(np.arange(n), np.arange(n)); DParam = np.array(dm[I > J], dtype=np.float32)`
+    (ripser.py, dense branch) -- the upper triangle in row-major order."""
+    import numpy as np
+    import torch
+    from tda_eeg_audio_b200.rips import condense
+    rng = np.random.default_rng(0)
+    for n in (2, 3, 5, 47, 64):
+        dm = rng.random((n, n))          # deliberately NOT symmetric: the order must pick dm[i, j], i < j
+        I, J = np.meshgrid(np.arange(n), np.arange(n))
+        dparam = np.array(dm[I > J], dtype=np.float32)
+        assert np.array_equal(condense(dm.astype(np.float32)), dparam)
+        assert np.array_equal(condense(torch.from_numpy(dm.astype(np.float32))[None]).numpy()[0], dparam)
+        iu = np.triu_indices(n, 1)
+        assert np.array_equal(dparam, dm[iu].astype(np.float32))
