@@ -156,3 +156,60 @@ def drivers_golden():
 
 if __name__ == "__main__":
     drivers_golden()
+
+
+def _notebook_functions(notebook, names, namespace):
+    """exec the named function definitions of a reference NOTEBOOK where it lies: the code cells are
+    parsed with ast (IPython magics dropped) and only the top-level `def`s asked for are executed --
+    the cells' own analysis code is not run and nothing is copied."""
+    import ast
+    import json
+    path = os.path.join(reference_import.REFERENCE_ROOT, "notebooks", notebook)
+    body = []
+    for cell in json.load(open(path))["cells"]:
+        if cell["cell_type"] != "code":
+            continue
+        src = "".join(cell["source"])
+        src = "\n".join(ln for ln in src.splitlines() if not ln.lstrip().startswith(("%", "!")))
+        try:
+            tree = ast.parse(src)
+        except SyntaxError:
+            continue
+        body += [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert {n.name for n in body} == set(names), (notebook, names, [n.name for n in body])
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), namespace)
+    return namespace
+
+
+def notebooks_golden():
+    """design/apply_bandpass_filter, create_sliding_windows (notebook 1) and compute_correlation_matrix,
+    correlation_to_distance (notebook 2) of the reference, on seeded inputs -> notebooks.npz."""
+    from scipy import signal
+    u = reference_import.load_utils()
+    ns = {"np": np, "signal": signal}
+    _notebook_functions("1_preprocesamiento.ipynb",
+                        ["design_bandpass_filter", "apply_bandpass_filter", "create_sliding_windows"], ns)
+    _notebook_functions("2_graph_construction.ipynb", ["compute_correlation_matrix", "correlation_to_distance"], ns)
+    rng = np.random.default_rng(20261018)
+    out = {}
+    x = rng.standard_normal((4, 8)) / np.sqrt(8) @ rng.standard_normal((8, 1000)) + 0.5 * rng.standard_normal((4, 1000))
+    out["x"] = x
+    for name, (lo, hi) in u.FREQ_BANDS.items():
+        out[f"sos_{name}"] = ns["design_bandpass_filter"](lo, hi, 250, 4)
+        out[f"filt_{name}"] = ns["apply_bandpass_filter"](x, lo, hi, 250, 4)
+    wins, times = ns["create_sliding_windows"](out["filt_alpha"], 1.0, 0.75, 250)
+    out["windows_alpha"], out["window_times"] = wins, times
+    w = rng.standard_normal((47, 8)) / np.sqrt(8) @ rng.standard_normal((8, 250)) + 0.5 * rng.standard_normal((47, 250))
+    w[5] = 2.5            # zero variance -> NaN -> 0
+    w[9] = w[8]           # duplicate channel -> r = 1 -> d = 0
+    out["window47"] = w
+    c = ns["compute_correlation_matrix"](w)
+    out["corr47"] = c
+    for m in ("euclidean", "abs", "standard", "sqrt"):
+        out[f"dist47_{m}"] = ns["correlation_to_distance"](c, method=m)
+    np.savez_compressed(os.path.join(HERE, "notebooks.npz"), **out)
+    print("notebooks.npz:", sorted(out)[:6], "...", wins.shape, c.shape)
+
+
+if __name__ == "__main__":
+    notebooks_golden()

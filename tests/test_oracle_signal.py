@@ -56,3 +56,27 @@ def test_resample_design_matches_scipy():
         ref = signal.resample_poly(x, up, down)
         assert len(ref) == n_out
         np.testing.assert_allclose(y, ref, rtol=0, atol=1e-13)
+
+
+def test_notebook_functions_match_reference_fixture():
+    """tests/golden/notebooks.npz holds the outputs of the reference's OWN notebook functions
+    (notebooks/1_preprocesamiento.ipynb: design/apply_bandpass_filter, create_sliding_windows;
+    notebooks/2_graph_construction.ipynb: compute_correlation_matrix, correlation_to_distance),
+    executed from the .ipynb where it lies (tests/golden/make_golden.py::notebooks_golden).  The
+    restatements the GPU parity tests compare against must reproduce them exactly."""
+    N = np.load(os.path.join(os.path.dirname(__file__), "golden", "notebooks.npz"))
+    x = N["x"]
+    for name, (lo, hi) in signal_ref.FREQ_BANDS.items():
+        assert np.array_equal(signal_ref.design_bandpass_filter(lo, hi, 250, 4), N[f"sos_{name}"])
+        assert np.array_equal(signal_ref.apply_bandpass_filter(x, lo, hi, 250), N[f"filt_{name}"])
+    wins, times = signal_ref.create_sliding_windows(N["filt_alpha"], 1.0, 0.75, 250)
+    assert np.array_equal(wins, N["windows_alpha"]) and np.array_equal(times, N["window_times"])
+    c = signal_ref.compute_correlation_matrix(N["window47"])
+    assert np.array_equal(c, N["corr47"])
+    assert (c[5] == 0).all() and c[8, 9] == 1.0          # zero-variance row -> 0, duplicate channel -> 1
+    for m in ("euclidean", "abs", "standard", "sqrt"):
+        assert np.array_equal(signal_ref.correlation_to_distance(N["corr47"], m), N[f"dist47_{m}"])
+    # the host-side design the CUDA filter is fed is the same call
+    from tda_eeg_audio_b200 import dsp
+    for name, (lo, hi) in signal_ref.FREQ_BANDS.items():
+        assert np.array_equal(dsp.design_bandpass_filter(lo, hi, 250, 4), N[f"sos_{name}"])
