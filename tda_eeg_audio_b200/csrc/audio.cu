@@ -209,7 +209,7 @@ extern "C" int tda_hilbert_envelope_f64(const double* x, long long n_seq, long l
     if (n_seq == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     double2* z = (double2*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
-    cufftHandle plan;
+    cufftHandle plan = 0;
     int rc = get_plan(T, n_seq, &plan);
     if (rc) return rc;
     if (cufftSetStream(plan, st) != CUFFT_SUCCESS) return 10000;
