@@ -225,6 +225,23 @@ def raw_eeg_workload(dev, R=256):
     res = {"recordings": R, "ms": round(ms, 3), "recordings_per_s": round(R / ms * 1e3, 1),
            "diagrams_per_s": round(R * N_BANDS * N_WIN / ms * 1e3, 1), "stage_ms": stages,
            "input_bytes": x.numel() * 8}
+    # the reference's own code path for the signal stages (scipy sosfiltfilt per channel, numpy corrcoef
+    # per window: notebooks 1-2, restated in oracle/signal_ref.py and pinned by tests/golden/notebooks.npz)
+    # on ONE recording, one process, as the reported CPU baseline of these stages
+    try:
+        import numpy as np
+        from oracle import signal_ref
+        x0 = x[0].cpu().numpy()
+        t0 = time.perf_counter()
+        ref = signal_ref.eeg_distances(x0, overlap=0.0)            # (5, 60, 47, 47) float64
+        cpu_ms = (time.perf_counter() - t0) * 1e3
+        got = D[0].double().cpu().numpy()
+        off = ~np.eye(N_CH, dtype=bool)
+        err = (np.abs(got - ref) / np.maximum(ref, 1e-30))[..., off].max()
+        res["cpu_signal_stages"] = {"ms_per_recording": round(cpu_ms, 1), "cores": 1, "kind": "port",
+                                    "max_rel_err_gpu_vs_cpu_distances": float(err)}
+    except Exception as exc:
+        res["cpu_signal_stages"] = {"error": repr(exc)}
     del x, D, st
     torch.cuda.empty_cache()
     return res
