@@ -81,19 +81,11 @@ int tda_rips_h01_batched(const float* D, int B, int N, int ld, long long strideB
                          float* bd0, long long* pr0, float* bd1, long long* pr1, int* counts,
                          int cap1, int* status, void* ws, size_t ws_bytes, void* stream);
 
-/* Rips H0+H1 for medium matrices, 2 <= N <= 254 (the Takens clouds of the audio path), one CTA per
- * cloud.  Same outputs and conventions as tda_rips_h01_batched; differences: `npts` (may be NULL)
- * gives the point count of every item (<= N, the leading npts x npts block of the ld x ld matrix
- * is used), and the H0 output has an explicit row capacity cap0 (bd0 (B, cap0, 2)).
- * Replaces ripser(...) inside compute_audio_persistence, /root/reference/scripts/utils.py:131. */
-size_t tda_rips_h01_medium_workspace_bytes(int B, int N);
-int tda_rips_h01_medium(const float* D, const int* npts, int B, int N, int ld, long long strideB,
-                        float thresh, float* bd0, long long* pr0, int cap0, float* bd1, long long* pr1,
-                        int cap1, int* counts, int* status, void* ws, size_t ws_bytes, void* stream);
-
 /* Rips H0+H1 for big clouds, 2 <= N <= 2048 (the 1,000-2,000 point Takens clouds of the scaling
- * stress, BASELINE.json configs[4]; also any batch above the 64-point engine).  Same arguments,
- * outputs and conventions as tda_rips_h01_medium.  Grid-wide cooperative phases over a chunk of
+ * stress, BASELINE.json configs[4]; the 97-248 point Takens clouds of the audio path; any batch
+ * above the 64-point engine).  Same outputs and conventions as tda_rips_h01_batched; differences:
+ * `npts` (may be NULL) gives the point count of every item (<= N, the leading npts x npts block of
+ * the ld x ld matrix is used), and the H0 output has an explicit row capacity cap0 (bd0 (B, cap0, 2)).  Grid-wide cooperative phases over a chunk of
  * clouds (edge keys, one device-wide radix sort, rank matrices, Kruskal, first-cofacet /
  * apparent-pair classification of every edge) followed by one CTA per cloud for the serial part
  * (cocycle sweep over the edges a live class can see).  The chunk size follows from `ws_bytes`;

@@ -34,8 +34,6 @@ SIGNATURES = {
     "tda_pairwise_dist_f32": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp]),
     "tda_wasserstein_batched": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _ll, _vp, _vp]),
     "tda_eeg_features_host": (_i, [_vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
-    "tda_rips_h01_medium_workspace_bytes": (_sz, [_i, _i]),
-    "tda_rips_h01_medium": (_i, [_vp, _vp, _i, _i, _i, _ll, _f, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "tda_rips_h01_large_workspace_bytes": (_sz, [_i, _i]),
     "tda_rips_h01_large": (_i, [_vp, _vp, _i, _i, _i, _ll, _f, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "tda_resample_poly_f64": (_i, [_vp, _ll, _ll, _ll, _i, _i, _vp, _i, _ll, _ll, _vp, _ll, _vp]),

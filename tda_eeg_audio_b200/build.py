@@ -65,7 +65,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         if r.returncode != 0:
             raise subprocess.CalledProcessError(r.returncode, f"nvcc {src}")
     objs = [_obj(s) for s in sources()]
-    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", LIB] + objs + ["-lcufft", "-Xlinker", "-rpath=/usr/local/cuda/lib64"])
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "--cudart", "shared", "-o", LIB] + objs + ["-lcufft", "-Xlinker", "-rpath=/usr/local/cuda/lib64"])
     return LIB
 
 

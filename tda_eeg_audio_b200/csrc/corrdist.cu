@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kThreads) corrdist_kernel(const double* __rest
     }
 }
 
-// corrdist_mma.cu: staged second generation (Gram on the FP64 tensor pipe), opt-in TDA_CORRDIST=mma
+// corrdist_mma.cu: the Gram on the FP64 tensor pipe (the default for the shapes it takes)
 int launch_corrdist_mma(const double* x, int R, int C, long long T, long long strideR, int win, int step, long long W,
                         int method, float* D, double* corr, long long strideO, cudaStream_t stream);
 
@@ -147,12 +147,11 @@ extern "C" int tda_corrdist_windows(const double* x, int R, int C, long long T, 
     if (strideR == 0) strideR = (long long)C * T;
     if (strideO == 0) strideO = W * (long long)C * C;
     {
-        const char* gen = getenv("TDA_CORRDIST");
-        if (gen && gen[0] == 'm') {
-            const int rc = launch_corrdist_mma(x, R, C, T, strideR, win, step, W, method, D, corr, strideO,
-                                               (cudaStream_t)stream);
-            if (rc != TDA_E_SIZE) return rc;   // shapes it does not take fall through to the first generation
-        }
+        // the Gram on the FP64 tensor pipe (corrdist_mma.cu) for every shape it takes (the 47 x 250
+        // EEG windows among them); the register-tile FMA kernel below serves the others
+        const int rc = launch_corrdist_mma(x, R, C, T, strideR, win, step, W, method, D, corr, strideO,
+                                           (cudaStream_t)stream);
+        if (rc != TDA_E_SIZE) return rc;
     }
     cudaError_t e = cudaFuncSetAttribute(corrdist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;

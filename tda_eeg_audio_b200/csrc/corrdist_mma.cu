@@ -1,10 +1,8 @@
-// corrdist_mma.cu — STAGED second generation of the window -> correlation -> distance kernel: the
-// Gram on the FP64 tensor pipe (mma.sync.m8n8k4.f64; tcgen05 has no FP64 kind, and FP64 is what the
-// accuracy needs: d = sqrt(2(1-r)) cancels as r -> 1, corrdist.cu / SURVEY.md §7.2 H3).
-//
-// STATUS: opt-in with TDA_CORRDIST=mma, compiled for sm_100a but NOT yet run on a GPU (the round's
-// GPU budget was spent before it was written); it is neither the default nor covered by a parity
-// run.  tools/ab_corrdist.py times it against corrdist_kernel and compares the outputs.
+// corrdist_mma.cu — the window -> correlation -> distance kernel with the Gram on the FP64 tensor
+// pipe (mma.sync.m8n8k4.f64; tcgen05 has no FP64 kind, and FP64 is what the accuracy needs:
+// d = sqrt(2(1-r)) cancels as r -> 1, corrdist.cu / SURVEY.md §7.2 H3).  Default for every shape it
+// takes; measured 2.1x the register-tile FMA kernel of corrdist.cu with bit-identical distances and
+// correlations (profiles/r02_staged_ab.jsonl).
 //
 // Same interface, same load / centring / epilogue arithmetic as corrdist_kernel (corrdist.cu), which
 // it replaces per window for:

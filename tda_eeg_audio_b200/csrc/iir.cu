@@ -11,11 +11,17 @@
 // update order in FP64, without FMA contraction, lands on the reference's numbers.
 //
 // Mapping: one thread owns one (band, sequence) job — the recursion is serial in time, and at the
-// benchmark shape there are 332,760 independent jobs.  A CTA of 128 jobs moves time tiles of 32
-// samples (now 16) through shared memory so that every HBM access is a coalesced 128-byte row segment
-// (lanes along time on the way in/out, lanes along jobs inside the recursion; odd row stride keeps
-// both conflict-free).  The forward pass materialises the padded intermediate once (workspace);
-// the backward pass walks the same tiles in reverse and writes only the un-padded samples.
+// benchmark shape there are 332,760 independent jobs.  A CTA of 128 jobs of ONE band (its
+// coefficients pinned in registers: the recursion's SASS is 36 DMUL/DADD per sample and nothing
+// else) moves time tiles of 16 samples through shared memory so that every HBM access is a
+// coalesced 128-byte row segment (lanes along time on the way in/out, lanes along jobs inside the
+// recursion; odd row stride keeps both conflict-free).  The staging is software-pipelined: while the
+// CTA runs the recursion on tile q, the sixteen values each thread contributes to tile q+1 are in
+// flight from HBM into its registers.  The forward pass materialises the padded intermediate once
+// (workspace); the backward pass walks the same tiles in reverse and writes only the un-padded
+// samples.  Measured against the two earlier generations of this kernel (coefficients from the
+// constant bank; unpipelined staging), outputs bit-equal: 27.9 / 16.8 / 9.9 ms for the five EEG bands
+// of 256 recordings (profiles/r02_staged_ab.jsonl).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -27,7 +33,7 @@ namespace tda {
 namespace iir {
 
 constexpr int kJobs = 128;   // threads per CTA = jobs per CTA
-constexpr int kTT = 16;      // samples per time tile (16: 34 KB of staging per CTA -> 6 CTAs = 24 warps per SM)
+constexpr int kTT = 16;      // samples per time tile (36 KB of staging per CTA)
 constexpr int kRPW = 32 / kTT;  // tile rows one warp moves per step
 constexpr int kLd = kTT + 1; // odd row stride
 constexpr int kMaxBands = 8;
@@ -42,49 +48,10 @@ struct Coef {
     int n;  // sections (form 0) or taps (form 1)
 };
 
-template <int FORM> struct State {
-    double z[8];
-    __device__ __forceinline__ void init(const Coef& cf, int band, double scale) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) z[k] = __dmul_rn(cf.zi[band][k], scale);
-    }
-    __device__ __forceinline__ double step(const Coef& cf, int band, double x) {
-        if (FORM == 0) {
-            // scipy _sosfilt: x_new = b0*x + z0 ; z0 = b1*x - a1*x_new + z1 ; z1 = b2*x - a2*x_new
-#pragma unroll
-            for (int s = 0; s < kMaxSec; ++s) {
-                if (s < cf.n) {
-                    const double* c = cf.c[band] + s * 6;
-                    const double xn = __dadd_rn(__dmul_rn(c[0], x), z[2 * s]);
-                    z[2 * s] = __dadd_rn(__dsub_rn(__dmul_rn(c[1], x), __dmul_rn(c[4], xn)), z[2 * s + 1]);
-                    z[2 * s + 1] = __dsub_rn(__dmul_rn(c[2], x), __dmul_rn(c[5], xn));
-                    x = xn;
-                }
-            }
-            return x;
-        } else {
-            // scipy lfilter (direct form II transposed):
-            //   y = Z[0] + b[0]*x ; Z[n] = Z[n+1] + x*b[n+1] - y*a[n+1] ; Z[last] = x*b[last] - y*a[last]
-            const double* b = cf.c[band];
-            const double* a = cf.c[band] + kMaxTaps;
-            const int nt = cf.n;
-            if (nt == 1) return __dmul_rn(x, b[0]);
-            const double y = __dadd_rn(z[0], __dmul_rn(b[0], x));
-#pragma unroll
-            for (int n = 0; n < kMaxTaps - 2; ++n) {
-                if (n < nt - 2)
-                    z[n] = __dsub_rn(__dadd_rn(z[n + 1], __dmul_rn(x, b[n + 1])), __dmul_rn(y, a[n + 1]));
-            }
-#pragma unroll
-            for (int n = 0; n < kMaxTaps - 1; ++n) {
-                if (n == nt - 2) z[n] = __dsub_rn(__dmul_rn(x, b[n + 1]), __dmul_rn(y, a[n + 1]));
-            }
-            return y;
-        }
-    }
-};
-
-// The same two recursions with the band's coefficients in registers (cr = Coef::c[band]).
+// The two recursions, the band's coefficients in registers (cr = Coef::c[band]):
+//   sos: scipy _sosfilt: x_new = b0*x + z0 ; z0 = b1*x - a1*x_new + z1 ; z1 = b2*x - a2*x_new
+//   ba : scipy lfilter (direct form II transposed):
+//        y = Z[0] + b[0]*x ; Z[n] = Z[n+1] + x*b[n+1] - y*a[n+1] ; Z[last] = x*b[last] - y*a[last]
 template <int FORM>
 __device__ __forceinline__ double step_regs(double (&z)[8], const double (&cr)[kMaxSec * 6], int n, double x) {
     if (FORM == 0) {
@@ -121,82 +88,11 @@ __device__ __forceinline__ double ext_value(const double* __restrict__ x, long l
     return __dsub_rn(__dmul_rn(2.0, x[T - 1]), x[T - 2 - (k - edge - T)]);
 }
 
-// jobs are (band, seq): job = band * n_seq + seq
+// jobs are (band, seq): job = band * n_seq + seq; a CTA works on groups of 128 sequences of one band
 //   forward : in = x (n_seq rows, stride x_stride), out = mid (n_jobs rows of Text)
 //   backward: in = mid, out = y (n_jobs rows of T, row stride T)
 template <int FORM, bool BACKWARD>
-__global__ void __launch_bounds__(kJobs) iir_pass_kernel(const double* __restrict__ in, double* __restrict__ out,
-                                                         long long n_seq, int n_bands, long long T, long long x_stride,
-                                                         int edge, const __grid_constant__ Coef cf) {
-    extern __shared__ __align__(16) double iir_smem[];
-    double* tin = iir_smem;
-    double* tout = iir_smem + kJobs * kLd;
-    const long long Text = T + 2LL * edge;
-    const long long n_jobs = n_seq * n_bands;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long n_tiles = (Text + kTT - 1) / kTT;
-    for (long long job0 = (long long)blockIdx.x * kJobs; job0 < n_jobs; job0 += (long long)gridDim.x * kJobs) {
-        const long long job = job0 + tid;
-        const bool active = job < n_jobs;
-        const int band = active ? (int)(job / n_seq) : 0;
-        State<FORM> st;
-        if (active) {
-            double scale;
-            if (!BACKWARD) scale = ext_value(in + (job % n_seq) * x_stride, T, edge, 0);
-            else scale = in[job * Text + (Text - 1)];
-            st.init(cf, band, scale);
-        }
-        for (long long q = 0; q < n_tiles; ++q) {
-            const long long tile = BACKWARD ? (n_tiles - 1 - q) : q;
-            const long long k0 = tile * kTT;
-            // ---- cooperative coalesced load: warp w takes rows w, w+4, ... ; lanes along time
-            for (int r = warp * kRPW + lane / kTT; r < kJobs; r += (kJobs / 32) * kRPW) {
-                const long long jb = job0 + r;
-                const int c = lane % kTT;
-                const long long k = k0 + c;
-                double v = 0.0;
-                if (jb < n_jobs && k < Text) {
-                    if (!BACKWARD) v = ext_value(in + (jb % n_seq) * x_stride, T, edge, k);
-                    else v = in[jb * Text + k];
-                }
-                tin[r * kLd + c] = v;
-            }
-            __syncthreads();
-            // ---- serial recursion, one job per thread
-            if (active) {
-                const int nvalid = (int)((Text - k0 < kTT) ? (Text - k0) : kTT);
-                if (!BACKWARD) {
-                    for (int c = 0; c < nvalid; ++c) tout[tid * kLd + c] = st.step(cf, band, tin[tid * kLd + c]);
-                } else {
-                    for (int c = nvalid - 1; c >= 0; --c) tout[tid * kLd + c] = st.step(cf, band, tin[tid * kLd + c]);
-                }
-            }
-            __syncthreads();
-            // ---- cooperative coalesced store
-            for (int r = warp * kRPW + lane / kTT; r < kJobs; r += (kJobs / 32) * kRPW) {
-                const long long jb = job0 + r;
-                const int c = lane % kTT;
-                const long long k = k0 + c;
-                if (jb < n_jobs && k < Text) {
-                    if (!BACKWARD) out[jb * Text + k] = tout[r * kLd + c];
-                    else if (k >= edge && k < edge + T) out[jb * T + (k - edge)] = tout[r * kLd + c];
-                }
-            }
-            // tin/tout of the next tile are written only after the next __syncthreads pair
-            __syncthreads();
-        }
-    }
-}
-
-// Second generation of the pass kernel (default; TDA_IIR=0 selects the first one for A/B runs): same
-// mapping and the same arithmetic, but the staging is software-pipelined.  While the CTA runs the
-// recursion on tile q out of shared memory, the sixteen values every thread contributes to tile q+1
-// are already on their way from HBM into its registers (independent, fully unrolled loads; the first
-// generation issued them one by one behind a 64-bit modulo each, and exposed the whole memory round
-// trip in front of every tile).  Row offsets are worked out once per group of jobs; two barriers per
-// tile instead of three.
-template <int FORM, bool BACKWARD>
-__global__ void __launch_bounds__(kJobs) iir_pass_kernel_v2(const double* __restrict__ in, double* __restrict__ out,
+__global__ void __launch_bounds__(kJobs, 4) iir_pass_kernel(const double* __restrict__ in, double* __restrict__ out,
                                                             long long n_seq, int n_bands, long long T,
                                                             long long x_stride, int edge,
                                                             const __grid_constant__ Coef cf) {
@@ -208,139 +104,38 @@ __global__ void __launch_bounds__(kJobs) iir_pass_kernel_v2(const double* __rest
     constexpr int kRows = kJobs / ((kJobs / 32) * kRPW);   // rows of a tile one thread moves (16)
     constexpr int kRStep = (kJobs / 32) * kRPW;            // distance between them (8)
     const long long Text = T + 2LL * edge;
-    const long long n_jobs = n_seq * n_bands;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r0 = warp * kRPW + lane / kTT;   // first tile row of this thread
     const int c = lane % kTT;                  // its column (time within the tile)
     const long long n_tiles = (Text + kTT - 1) / kTT;
-    for (long long job0 = (long long)blockIdx.x * kJobs; job0 < n_jobs; job0 += (long long)gridDim.x * kJobs) {
-        const long long job = job0 + tid;
-        const bool active = job < n_jobs;
-        const int band = active ? (int)(job / n_seq) : 0;
-        __syncthreads();   // the previous group's last tile has left tin / tout / the offset tables
-        inbase[tid] = active ? (BACKWARD ? job * Text : (job - (long long)band * n_seq) * x_stride) : 0;
-        outbase[tid] = active ? (BACKWARD ? job * T : job * Text) : 0;
-        State<FORM> st;
-        if (active) {
-            double scale;
-            if (!BACKWARD) scale = ext_value(in + (job - (long long)band * n_seq) * x_stride, T, edge, 0);
-            else scale = in[job * Text + (Text - 1)];
-            st.init(cf, band, scale);
-        }
-        __syncthreads();
-        const int rows_here = (int)((n_jobs - job0 < kJobs) ? (n_jobs - job0) : kJobs);
-        double nx[kRows];
-        // values of tile `tile` this thread stages: rows r0, r0 + 8, ..., column c
-        auto fetch = [&](long long tile) {
-            const long long k = tile * kTT + c;
-            const bool interior = BACKWARD || (tile * kTT >= edge && tile * kTT + kTT <= edge + T);
-#pragma unroll
-            for (int i = 0; i < kRows; ++i) {
-                const int r = r0 + kRStep * i;
-                double v = 0.0;
-                if (r < rows_here && k < Text) {
-                    const double* row = in + inbase[r];
-                    if (BACKWARD) v = row[k];
-                    else if (interior) v = row[k - edge];
-                    else v = ext_value(row, T, edge, k);
-                }
-                nx[i] = v;
-            }
-        };
-        fetch(BACKWARD ? n_tiles - 1 : 0);
-#pragma unroll
-        for (int i = 0; i < kRows; ++i) tin[(r0 + kRStep * i) * kLd + c] = nx[i];
-        __syncthreads();
-        for (long long q = 0; q < n_tiles; ++q) {
-            const long long tile = BACKWARD ? (n_tiles - 1 - q) : q;
-            const long long k0 = tile * kTT;
-            if (q + 1 < n_tiles) fetch(BACKWARD ? tile - 1 : tile + 1);   // in flight during the recursion
-            // ---- serial recursion, one job per thread
-            if (active) {
-                const int nvalid = (int)((Text - k0 < kTT) ? (Text - k0) : kTT);
-                if (!BACKWARD) {
-                    for (int cc = 0; cc < nvalid; ++cc) tout[tid * kLd + cc] = st.step(cf, band, tin[tid * kLd + cc]);
-                } else {
-                    for (int cc = nvalid - 1; cc >= 0; --cc) tout[tid * kLd + cc] = st.step(cf, band, tin[tid * kLd + cc]);
-                }
-            }
-            __syncthreads();   // tout complete, tin consumed
-            // ---- cooperative coalesced store of tile q, then the staged tile q + 1 takes tin
-            {
-                const long long k = k0 + c;
-                const bool keep = BACKWARD ? (k >= edge && k < edge + T) : (k < Text);
-                const long long ko = BACKWARD ? k - edge : k;
-#pragma unroll
-                for (int i = 0; i < kRows; ++i) {
-                    const int r = r0 + kRStep * i;
-                    if (keep && r < rows_here) out[outbase[r] + ko] = tout[r * kLd + c];
-                }
-            }
-            if (q + 1 < n_tiles) {
-#pragma unroll
-                for (int i = 0; i < kRows; ++i) tin[(r0 + kRStep * i) * kLd + c] = nx[i];
-            }
-            __syncthreads();   // tin holds tile q + 1, tout is free
-        }
-    }
-}
-
-// Third generation, STAGED: opt-in with TDA_IIR=3, compiled but not yet run on a GPU (the round's
-// GPU budget was spent), so it is neither the default nor covered by a parity run.  The second
-// generation with two changes: every group of 128 jobs belongs to ONE band, and that band's
-// coefficients are pinned in registers for the whole group instead of being fetched from the
-// constant bank at every use (20 loads next to the 36 FP64 operations of a sample in the sos form);
-// 4 CTAs per SM instead of 6.  tools/ab_iir.py measures it against the other two and compares bits.
-template <int FORM, bool BACKWARD>
-__global__ void __launch_bounds__(kJobs, 4) iir_pass_kernel_v3(const double* __restrict__ in, double* __restrict__ out,
-                                                            long long n_seq, int n_bands, long long T,
-                                                            long long x_stride, int edge,
-                                                            const __grid_constant__ Coef cf) {
-    extern __shared__ __align__(16) double iir_smem[];
-    double* tin = iir_smem;
-    double* tout = iir_smem + kJobs * kLd;
-    long long* inbase = reinterpret_cast<long long*>(iir_smem + 2 * kJobs * kLd);   // element offset of a job's input row
-    long long* outbase = inbase + kJobs;                                             // ... of its output row
-    constexpr int kRows = kJobs / ((kJobs / 32) * kRPW);   // rows of a tile one thread moves (16)
-    constexpr int kRStep = (kJobs / 32) * kRPW;            // distance between them (8)
-    const long long Text = T + 2LL * edge;
-    const long long n_jobs = n_seq * n_bands;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int r0 = warp * kRPW + lane / kTT;   // first tile row of this thread
-    const int c = lane % kTT;                  // its column (time within the tile)
-    const long long n_tiles = (Text + kTT - 1) / kTT;
-    // job groups: RC -> ceil(n_seq / 128) groups per band, each within one band; else consecutive jobs
+    // job groups: ceil(n_seq / 128) groups per band, each within one band
     const long long gpb = (n_seq + kJobs - 1) / kJobs;
-    constexpr bool RC = true;
-    const long long n_groups = RC ? gpb * n_bands : (n_jobs + kJobs - 1) / kJobs;
+    const long long n_groups = gpb * n_bands;
     for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-        const int gband = RC ? (int)(grp / gpb) : 0;                                  // uniform in the CTA
-        const long long seq0 = RC ? (grp - (long long)gband * gpb) * kJobs : 0;
-        const long long job0 = RC ? (long long)gband * n_seq + seq0 : grp * kJobs;
-        const long long job = job0 + tid;
-        const bool active = RC ? (seq0 + tid < n_seq) : (job < n_jobs);
-        const int band = RC ? gband : (active ? (int)(job / n_seq) : 0);
+        const int band = (int)(grp / gpb);                                   // uniform in the CTA
+        const long long seq0 = (grp - (long long)band * gpb) * kJobs;
+        const long long job = (long long)band * n_seq + seq0 + tid;
+        const bool active = seq0 + tid < n_seq;
         double cr[kMaxSec * 6];
-        if (RC) {
 #pragma unroll
-            for (int k = 0; k < kMaxSec * 6; ++k) {
-                const bool used = FORM == 0 ? (k % 6 != 3) : (k < 2 * kMaxTaps);
-                cr[k] = used ? cf.c[band][k] : 0.0;
-                if (used) asm volatile("" : "+d"(cr[k]));   // a register, not a constant-bank operand
-            }
+        for (int k = 0; k < kMaxSec * 6; ++k) {
+            const bool used = FORM == 0 ? (k % 6 != 3) : (k < 2 * kMaxTaps);
+            cr[k] = used ? cf.c[band][k] : 0.0;
+            if (used) asm volatile("" : "+d"(cr[k]));   // a register, not a constant-bank operand
         }
         __syncthreads();   // the previous group's last tile has left tin / tout / the offset tables
-        inbase[tid] = active ? (BACKWARD ? job * Text : (job - (long long)band * n_seq) * x_stride) : 0;
+        inbase[tid] = active ? (BACKWARD ? job * Text : (seq0 + tid) * x_stride) : 0;
         outbase[tid] = active ? (BACKWARD ? job * T : job * Text) : 0;
-        State<FORM> st;
+        double z[8];
         if (active) {
             double scale;
-            if (!BACKWARD) scale = ext_value(in + (job - (long long)band * n_seq) * x_stride, T, edge, 0);
+            if (!BACKWARD) scale = ext_value(in + (seq0 + tid) * x_stride, T, edge, 0);
             else scale = in[job * Text + (Text - 1)];
-            st.init(cf, band, scale);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) z[k] = __dmul_rn(cf.zi[band][k], scale);
         }
         __syncthreads();
-        const long long left = RC ? n_seq - seq0 : n_jobs - job0;
+        const long long left = n_seq - seq0;
         const int rows_here = (int)(left < kJobs ? left : kJobs);
         double nx[kRows];
         // values of tile `tile` this thread stages: rows r0, r0 + 8, ..., column c
@@ -371,18 +166,12 @@ __global__ void __launch_bounds__(kJobs, 4) iir_pass_kernel_v3(const double* __r
             // ---- serial recursion, one job per thread
             if (active) {
                 const int nvalid = (int)((Text - k0 < kTT) ? (Text - k0) : kTT);
-                if (RC) {
-                    if (!BACKWARD) {
-                        for (int cc = 0; cc < nvalid; ++cc)
-                            tout[tid * kLd + cc] = step_regs<FORM>(st.z, cr, cf.n, tin[tid * kLd + cc]);
-                    } else {
-                        for (int cc = nvalid - 1; cc >= 0; --cc)
-                            tout[tid * kLd + cc] = step_regs<FORM>(st.z, cr, cf.n, tin[tid * kLd + cc]);
-                    }
-                } else if (!BACKWARD) {
-                    for (int cc = 0; cc < nvalid; ++cc) tout[tid * kLd + cc] = st.step(cf, band, tin[tid * kLd + cc]);
+                if (!BACKWARD) {
+                    for (int cc = 0; cc < nvalid; ++cc)
+                        tout[tid * kLd + cc] = step_regs<FORM>(z, cr, cf.n, tin[tid * kLd + cc]);
                 } else {
-                    for (int cc = nvalid - 1; cc >= 0; --cc) tout[tid * kLd + cc] = st.step(cf, band, tin[tid * kLd + cc]);
+                    for (int cc = nvalid - 1; cc >= 0; --cc)
+                        tout[tid * kLd + cc] = step_regs<FORM>(z, cr, cf.n, tin[tid * kLd + cc]);
                 }
             }
             __syncthreads();   // tout complete, tin consumed
@@ -449,62 +238,31 @@ extern "C" int tda_filtfilt_f64(const double* x, long long n_seq, long long T, l
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long n_jobs = n_seq * n_bands;
-    long long blocks = (n_jobs + kJobs - 1) / kJobs;
-    const long long maxb = (long long)sms * 6;  // 34 KB of staging per CTA -> 6 CTAs per SM
-    if (blocks > maxb) blocks = maxb;
+    const long long groups = ((n_seq + kJobs - 1) / kJobs) * n_bands;
+    const long long maxb = (long long)sms * 4;  // 128 registers, 36 KB of staging per CTA -> 4 CTAs per SM
+    const int grid = (int)(groups < maxb ? groups : maxb);
     cudaStream_t st = (cudaStream_t)stream;
     double* mid = (double*)ws;
-    // TDA_IIR=0: first-generation kernel (A/B measurements)
-    const char* gen = getenv("TDA_IIR");
-    const bool v2 = !(gen && gen[0] == '0');
-    const bool v3 = gen && gen[0] == '3';   // staged third generation (register coefficients), opt-in
-    if (v3) {
-        const long long groups = ((n_seq + kJobs - 1) / kJobs) * n_bands;
-        blocks = groups < (long long)sms * 4 ? groups : (long long)sms * 4;
+    const int smem = 2 * kJobs * kLd * (int)sizeof(double) + 2 * kJobs * (int)sizeof(long long);
+    if (form == 0) {
+        cudaFuncSetAttribute(iir_pass_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(iir_pass_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    } else {
+        cudaFuncSetAttribute(iir_pass_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(iir_pass_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     }
-    const int smem = 2 * kJobs * kLd * (int)sizeof(double) + (v2 ? 2 * kJobs * (int)sizeof(long long) : 0);
-    cudaFuncSetAttribute(iir_pass_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(iir_pass_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(iir_pass_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(iir_pass_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(iir_pass_kernel_v2<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(iir_pass_kernel_v2<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(iir_pass_kernel_v2<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(iir_pass_kernel_v2<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(iir_pass_kernel_v3<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(iir_pass_kernel_v3<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(iir_pass_kernel_v3<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(iir_pass_kernel_v3<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    const int grid = (int)blocks;
     {
         tda::ProfScope prof(form == 0 ? "iir_sos_forward" : "iir_ba_forward", st);
-        if (v3) {
-            if (form == 0) iir_pass_kernel_v3<0, false><<<grid, kJobs, smem, st>>>(x, mid, n_seq, n_bands, T, x_stride, padlen, cf);
-            else iir_pass_kernel_v3<1, false><<<grid, kJobs, smem, st>>>(x, mid, n_seq, n_bands, T, x_stride, padlen, cf);
-        } else if (v2) {
-            if (form == 0) iir_pass_kernel_v2<0, false><<<grid, kJobs, smem, st>>>(x, mid, n_seq, n_bands, T, x_stride, padlen, cf);
-            else iir_pass_kernel_v2<1, false><<<grid, kJobs, smem, st>>>(x, mid, n_seq, n_bands, T, x_stride, padlen, cf);
-        } else {
-            if (form == 0) iir_pass_kernel<0, false><<<grid, kJobs, smem, st>>>(x, mid, n_seq, n_bands, T, x_stride, padlen, cf);
-            else iir_pass_kernel<1, false><<<grid, kJobs, smem, st>>>(x, mid, n_seq, n_bands, T, x_stride, padlen, cf);
-        }
+        if (form == 0) iir_pass_kernel<0, false><<<grid, kJobs, smem, st>>>(x, mid, n_seq, n_bands, T, x_stride, padlen, cf);
+        else iir_pass_kernel<1, false><<<grid, kJobs, smem, st>>>(x, mid, n_seq, n_bands, T, x_stride, padlen, cf);
         tda::count_launch();
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     {
         tda::ProfScope prof(form == 0 ? "iir_sos_backward" : "iir_ba_backward", st);
-        if (v3) {
-            if (form == 0) iir_pass_kernel_v3<0, true><<<grid, kJobs, smem, st>>>(mid, y, n_seq, n_bands, T, 0, padlen, cf);
-            else iir_pass_kernel_v3<1, true><<<grid, kJobs, smem, st>>>(mid, y, n_seq, n_bands, T, 0, padlen, cf);
-        } else if (v2) {
-            if (form == 0) iir_pass_kernel_v2<0, true><<<grid, kJobs, smem, st>>>(mid, y, n_seq, n_bands, T, 0, padlen, cf);
-            else iir_pass_kernel_v2<1, true><<<grid, kJobs, smem, st>>>(mid, y, n_seq, n_bands, T, 0, padlen, cf);
-        } else {
-            if (form == 0) iir_pass_kernel<0, true><<<grid, kJobs, smem, st>>>(mid, y, n_seq, n_bands, T, 0, padlen, cf);
-            else iir_pass_kernel<1, true><<<grid, kJobs, smem, st>>>(mid, y, n_seq, n_bands, T, 0, padlen, cf);
-        }
+        if (form == 0) iir_pass_kernel<0, true><<<grid, kJobs, smem, st>>>(mid, y, n_seq, n_bands, T, 0, padlen, cf);
+        else iir_pass_kernel<1, true><<<grid, kJobs, smem, st>>>(mid, y, n_seq, n_bands, T, 0, padlen, cf);
         tda::count_launch();
     }
     return (int)cudaGetLastError();

@@ -1,6 +1,6 @@
 // rips_large.cu — Vietoris–Rips H0+H1 (Z/2) for batches of big clouds (N <= 2048): the
 // scaling-stress Takens clouds of 1,000-2,000 points (BASELINE.json configs[4]) and, because the
-// algorithm does far less serial work than the CTA-per-cloud sweep of rips_medium.cu, any batch
+// algorithm does far less serial work than a CTA-per-cloud sweep over every edge, any batch
 // of clouds above the 64-point engine.
 //
 // Replaces ripser.ripser(point_cloud / dm, maxdim=1, thresh) as called by
@@ -821,7 +821,6 @@ static int tier1_ctas_per_sm(int N, int nth) {
     int r = by_threads < by_smem ? by_threads : by_smem;
     if (N > 256 && r > 2) r = 2;  // ~128 registers per thread with several apexes per thread
     if (nth == 64 && r > 12) r = 12;  // measured: 129-256 points run best with 12 two-warp CTAs per SM
-    if (const char* ev = getenv("TDA_LARGE_CTAS")) { int v = atoi(ev); if (v >= 1 && v < r) r = v; }   // tuning knob
     return r < 1 ? 1 : r;
 }
 

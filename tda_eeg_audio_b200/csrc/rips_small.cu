@@ -964,65 +964,40 @@ extern "C" int tda_rips_h01_batched(const float* D, int B, int N, int ld, long l
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms > 148) sms = 148;
-    // TDA_RIPS_ENGINE=bits selects the alternative tiers 1-2 of rips_bits.cu (lane = class bit-matrix
-    // sweep: a second, independently written implementation, parity-tested, ~8 % slower on EEG windows)
-    const char* eng = getenv("TDA_RIPS_ENGINE");
-    if (!(eng && eng[0] == 'b')) {
-        // tiers 1-2: PHI per edge, lanes = apexes
-        const char* w1 = getenv("TDA_RIPS_W1");   // "0" switches the one-word tier off (A/B measurements)
-        const bool tier0 = (N == 47) && !(w1 && w1[0] == '0');
-        if (tier0) {
-            // 47-point windows rarely hold more than 32 classes at once: a one-word tier first
-            p.worklist = nullptr; p.n_work = nullptr;
-            p.overflow_list = (int*)(w8 + wl.list2); p.n_overflow = counters + 2;
-            p.rec_global = (uint32_t*)(w8 + wl.rec0);
-            // TDA_RIPS_OPT (A/B measurements): warps per CTA of the first tier, two CTAs per SM.  8 = two
-            // sort buffers; 10, 11, 12 = register sort with a fixed budget of shared memory per window
-            const char* os = getenv("TDA_RIPS_OPT");
-            int wpb = os ? atoi(os) : 12;
-            if (wpb != 8 && wpb != 10 && wpb != 11) wpb = 12;
-            const int per_sm = 2;
-            long long need = ((long long)B + wpb - 1) / wpb;
-            int grid = (int)((long long)sms * per_sm < need ? (long long)sms * per_sm : need);
-            switch (wpb) {
-                case 8: e = launch_tier<1, false, 47, 0>(p, wpb, grid, st); break;
-                case 10: e = launch_tier<1, false, 47, 10>(p, wpb, grid, st); break;
-                case 11: e = launch_tier<1, false, 47, 11>(p, wpb, grid, st); break;
-                default: e = launch_tier<1, false, 47, 12>(p, wpb, grid, st); break;
-            }
-            if (e != cudaSuccess) return (int)e;
-        }
-        {
-            p.worklist = tier0 ? (const int*)(w8 + wl.list2) : nullptr; p.n_work = tier0 ? counters + 2 : nullptr;
-            p.overflow_list = (int*)(w8 + wl.list1); p.n_overflow = counters + 0;
-            int wpb = (int)(((227 * 1024) / 2 - 1024) / Layout<2, false>::bytes(N));
-            if (wpb < 1) wpb = 1;
-            if (wpb > 8) wpb = 8;
-            size_t smem = Layout<2, false>::bytes(N) * wpb;
-            int per_sm = (int)((227 * 1024) / (smem + 1024));
-            if (per_sm < 1) per_sm = 1;
-            if (per_sm > 2) per_sm = 2;
-            long long need = tier0 ? (long long)sms * per_sm : ((long long)B + wpb - 1) / wpb;
-            int grid = (int)((long long)sms * per_sm < need ? (long long)sms * per_sm : need);
-            e = (N == 47) ? launch_tier<2, false, 47>(p, wpb, grid, st) : launch_tier<2, false, 0>(p, wpb, grid, st);
-            if (e != cudaSuccess) return (int)e;
-        }
-        {
-            p.worklist = (const int*)(w8 + wl.list1); p.n_work = counters + 0;
-            p.overflow_list = (int*)(w8 + wl.list2); p.n_overflow = counters + 1;
-            e = launch_tier<4, false, 0>(p, 2, sms * 2, st);
-            if (e != cudaSuccess) return (int)e;
-        }
-    } else {
-        // tier 1: class-per-lane bit-matrix sweep, 32 simultaneous classes (rips_bits.cu)
+    // tiers 1-2: PHI per edge, lanes = apexes
+    const bool tier0 = (N == 47);
+    if (tier0) {
+        // 47-point windows rarely hold more than 32 classes at once: a one-word tier first (register
+        // sort, twelve warps per CTA, two CTAs per SM)
         p.worklist = nullptr; p.n_work = nullptr;
-        p.overflow_list = (int*)(w8 + wl.list1); p.n_overflow = counters + 0;
-        e = launch_bits_tier(p, 1, sms, st);
+        p.overflow_list = (int*)(w8 + wl.list2); p.n_overflow = counters + 2;
+        p.rec_global = (uint32_t*)(w8 + wl.rec0);
+        constexpr int wpb = 12;
+        const int per_sm = 2;
+        long long need = ((long long)B + wpb - 1) / wpb;
+        int grid = (int)((long long)sms * per_sm < need ? (long long)sms * per_sm : need);
+        e = launch_tier<1, false, 47, wpb>(p, wpb, grid, st);
         if (e != cudaSuccess) return (int)e;
-        // tier 2: the same with 64 classes on the windows tier 1 gave up on
+    }
+    {
+        p.worklist = tier0 ? (const int*)(w8 + wl.list2) : nullptr; p.n_work = tier0 ? counters + 2 : nullptr;
+        p.overflow_list = (int*)(w8 + wl.list1); p.n_overflow = counters + 0;
+        int wpb = (int)(((227 * 1024) / 2 - 1024) / Layout<2, false>::bytes(N));
+        if (wpb < 1) wpb = 1;
+        if (wpb > 8) wpb = 8;
+        size_t smem = Layout<2, false>::bytes(N) * wpb;
+        int per_sm = (int)((227 * 1024) / (smem + 1024));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 2) per_sm = 2;
+        long long need = tier0 ? (long long)sms * per_sm : ((long long)B + wpb - 1) / wpb;
+        int grid = (int)((long long)sms * per_sm < need ? (long long)sms * per_sm : need);
+        e = (N == 47) ? launch_tier<2, false, 47>(p, wpb, grid, st) : launch_tier<2, false, 0>(p, wpb, grid, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    {
         p.worklist = (const int*)(w8 + wl.list1); p.n_work = counters + 0;
         p.overflow_list = (int*)(w8 + wl.list2); p.n_overflow = counters + 1;
-        e = launch_bits_tier(p, 2, sms, st);
+        e = launch_tier<4, false, 0>(p, 2, sms * 2, st);
         if (e != cudaSuccess) return (int)e;
     }
     // tier 3: W=64 with PHI in global scratch, handles every N<=64 input

@@ -1,6 +1,4 @@
-// rips_small.cuh — declarations shared by the two kernel families of the N <= 64 Rips engine
-// (rips_bits.cu: class-per-lane bit-matrix sweep, tiers 1-2; rips_small.cu: PHI-per-edge sweep,
-// the capacity tier that handles every input).
+// rips_small.cuh — declarations of the N <= 64 Rips engine (rips_small.cu).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -66,10 +64,6 @@ __device__ __forceinline__ int tri_index(int x, int y, int z) {
     const int a = max(x, max(y, z)), c = min(x, min(y, z)), b = x + y + z - a - c;
     return c3(a) + c2(b) + c;
 }
-
-// tiers 1-2 (rips_bits.cu): cpl = classes per lane (1 => 32 simultaneous classes, 2 => 64)
-cudaError_t launch_bits_tier(const Params& p, int cpl, int sms, cudaStream_t st);
-size_t bits_tier_warp_bytes(int N, int cpl);
 
 }  // namespace rips_small
 }  // namespace tda

@@ -37,8 +37,7 @@ def rips_h01_batched(D, thresh=float("inf"), cap1=None, want_pairs=True, out=Non
     FFI format, half the bytes.
 
     engine="auto": N <= 64 runs the warp-per-window engine (rips_small), larger N (or ragged
-    batches) the grid-cooperative engine (rips_large, 4-6x the throughput of the older
-    CTA-per-cloud engine, which stays available as engine="medium" for N <= 254).  `npts` (CUDA int32 (B,), medium / large engines)
+    batches) the grid-cooperative engine (rips_large).  `npts` (CUDA int32 (B,), large engine)
     gives per-item point counts for padded batches.  Returns dict of CUDA tensors: bd0 (B,N,2) f32, pr0 (B,N,2) i64,
     bd1 (B,cap1,2) f32, pr1 (B,cap1,2) i64, counts (B,2) i32, status (B,) i32 — layout of
     include/tda_b200.h.
@@ -87,8 +86,6 @@ def rips_h01_batched(D, thresh=float("inf"), cap1=None, want_pairs=True, out=Non
     status = buf("status", (B,), torch.int32)
     if engine == "small":
         wsb = int(lib.tda_rips_h01_workspace_bytes(B, N))
-    elif engine == "medium":
-        wsb = int(lib.tda_rips_h01_medium_workspace_bytes(B, N))
     elif engine == "large":
         wsb = int(lib.tda_rips_h01_large_workspace_bytes(B, N))
     else:
@@ -108,8 +105,7 @@ def rips_h01_batched(D, thresh=float("inf"), cap1=None, want_pairs=True, out=Non
             if npts is not None:
                 assert npts.is_cuda and npts.dtype == torch.int32 and npts.shape == (B,)
                 npts = npts.contiguous()
-            fn = lib.tda_rips_h01_medium if engine == "medium" else lib.tda_rips_h01_large
-            rc = fn(
+            rc = lib.tda_rips_h01_large(
                 D.data_ptr(), _ptr(npts), B, N, D.stride(1), sB, float(thresh), bd0.data_ptr(), _ptr(pr0), N,
                 bd1.data_ptr(), _ptr(pr1), cap1, counts.data_ptr(), status.data_ptr(), ws.data_ptr(), wsb, stream)
     _lib.check(rc, "tda_rips_h01_" + engine)

@@ -66,7 +66,6 @@ def test_argument_errors_of_the_cloud_and_audio_entry_points():
     lib = _lib.load()
     assert lib.tda_rips_h01_large_workspace_bytes(4, 2049) == 0
     assert lib.tda_rips_h01_large_workspace_bytes(4, 300) > 0
-    assert lib.tda_rips_h01_medium_workspace_bytes(4, 255) == 0
     assert lib.tda_rips_h01_large(None, None, 1, 300, 300, 0, 2.0, None, None, 300, None, None, 8, None, None, None, 0, None) == -1
     assert lib.tda_resample_poly_f64(None, 1, 10, 10, 5, 882, None, 3529, 10, 15, None, 15, None) == -1
     assert lib.tda_hilbert_envelope_workspace_bytes(2, 15000) >= 2 * 15000 * 16

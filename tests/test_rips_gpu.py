@@ -210,23 +210,6 @@ def test_ripser_shim(cuda):
         ripser(np.zeros((3, 4)), distance_matrix=True)
 
 
-def test_alternative_class_per_lane_tiers(cuda, monkeypatch):
-    """TDA_RIPS_ENGINE=bits: the lane = class bit-matrix sweep of rips_bits.cu (a second, independently
-    written implementation of tiers 1-2) under the same bit-exact bar."""
-    monkeypatch.setenv("TDA_RIPS_ENGINE", "bits")
-    rng = np.random.default_rng(21)
-    g, _ = _compare(inputs.eeg_like(rng, 256), 2.0)
-    assert (g["status"] == 0).all()
-    _compare(inputs.sym_uniform(rng, 128, 47), 2.0)          # > 32 and > 64 simultaneous classes: all three tiers
-    for n in (3, 33, 47, 64):
-        D = inputs.sym_uniform(rng, 32, n)
-        _compare(D, np.inf)
-        _compare(D, 0.5)
-        _compare((np.round(D * 8) / 8).astype(np.float32), np.inf)
-    _compare(inputs.circle_cloud(rng, 32, 40), 0.9)
-    _compare(np.ones((2, 47, 47), np.float32) - np.eye(47, dtype=np.float32), 2.0)
-
-
 def test_h0_is_the_minimum_spanning_tree(cuda):
     """independent anchor at the EEG size: finite H0 deaths == scipy's MST weights, window by window"""
     import torch
@@ -270,6 +253,4 @@ def test_known_answers_from_theory(cuda):
         if n <= 64:
             check(name, Dg, thr, h0, h1)
             check(name + "/condensed", condense(Dg), thr, h0, h1, n_points=n)
-        if n <= 254:
-            check(name + "/medium", Dg, thr, h0, h1, engine="medium")
         check(name + "/large", Dg, thr, h0, h1, engine="large")
