@@ -188,6 +188,17 @@ int tda_corr_to_dist_f64(const double* corr, int n, int method, double* dist, vo
  * (/root/reference/scripts/tda_eeg_classification_v2.py:166-168) before ripser's float32 cast. */
 int tda_symmetrize_f64_to_f32(const double* D, long long B, int n, float* out, void* stream);
 
+/* Input checker of the feature path, batched: validate_distance_matrix
+ * (/root/reference/scripts/tda_eeg_classification_v2.py:110-140) for B float64 n x n matrices at once.
+ * flags[b] = TDA_DM_* bits; stats (B, 3) float64 = { max |D - D^T|, min D, max |diag D| } (the numbers
+ * the reference prints in its messages; NaN as soon as one NaN is involved, like np.max / np.min). */
+#define TDA_DM_ASYMMETRIC 1 /* not np.allclose(D, D.T, rtol=1e-5, atol=1e-8)  */
+#define TDA_DM_NEGATIVE 2   /* an entry below -1e-10                          */
+#define TDA_DM_DIAGONAL 4   /* not np.allclose(diag, 0, atol=1e-10)           */
+#define TDA_DM_NAN 8
+#define TDA_DM_INF 16
+int tda_validate_distance_f64(const double* D, long long B, int n, int* flags, double* stats, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Audio side: delay, Takens embedding, pairwise distances.
  * tda_compute_tau     replaces compute_tau  /root/reference/scripts/utils.py:92-104
@@ -224,12 +235,18 @@ int tda_pairwise_dist_f32(const double* pts, const int* npts, long long B, int l
 int tda_wasserstein_batched(const float* bdA, const int* nA, int nA_stride, int capA, int limA,
                             const float* bdB, const int* nB, int nB_stride, int capB, int limB,
                             const int* idxA, const int* idxB, long long B, double* out, void* stream);
+/* The same for float64 diagrams (persim.wasserstein works in float64; the drop-in call
+ * wasserstein(dgm1, dgm2) of arbitrary diagrams goes through this entry, so nothing is rounded). */
+int tda_wasserstein_batched_f64(const double* bdA, const int* nA, int nA_stride, int capA, int limA,
+                                const double* bdB, const int* nB, int nB_stride, int capB, int limB,
+                                const int* idxA, const int* idxB, long long B, double* out, void* stream);
 
 /* End-to-end host entry for the EEG feature path: host distance matrices in, host feature table
  * out (process_file_features, /root/reference/scripts/tda_eeg_classification_v2.py:338-442, for
  * R recordings x Bd bands x Wn windows at once).  D (R,Bd,Wn,N,N) float32 HOST.  Optional host
  * outputs (NULL to skip): bd0 (B,N,2), bd1 (B,cap1,2), counts (B,2), status (B), feats (B,2,11);
- * table (R, Bd*44) float64 is mandatory.  Chunked over three streams; returns when done. */
+ * table (R, Bd*44) float64 is mandatory.  Chunked over three streams; returns when done.  The
+ * staging buffers and streams are cached per `device` ordinal, so one process may call with several. */
 int tda_eeg_features_host(const float* D, int R, int Bd, int Wn, int N, float thresh, int cap1,
                           float* bd0, float* bd1, int* counts, int* status, double* feats,
                           double* table, int device);
@@ -237,6 +254,15 @@ int tda_eeg_features_host(const float* D, int R, int Bd, int Wn, int N, float th
 int tda_eeg_features_condensed_host(const float* Dc, int R, int Bd, int Wn, int N, float thresh,
                                     int cap1, float* bd0, float* bd1, int* counts, int* status,
                                     double* feats, double* table, int device);
+/* The same with the argument type the reference's own per-window call receives: D64 (R,Bd,Wn,N,N)
+ * float64 HOST, as compute_eeg_persistence(dm) / compute_persistence_diagram(distance_matrix) take it
+ * (/root/reference/scripts/utils.py:135-141, tda_eeg_classification_v2.py:143-176).  Every chunk is
+ * symmetrised ((D + D^T)/2), its diagonal zeroed, clamped at 0 and cast to float32 on the device
+ * (tda_symmetrize_f64_to_f32) -- the preparation those functions do on the host -- before the Rips
+ * kernels.  Twice the PCIe bytes of the float32 entry. */
+int tda_eeg_features_f64_host(const double* D64, int R, int Bd, int Wn, int N, float thresh, int cap1,
+                              float* bd0, float* bd1, int* counts, int* status, double* feats,
+                              double* table, int device);
 
 #ifdef __cplusplus
 }

@@ -29,10 +29,12 @@ SIGNATURES = {
     "tda_corrdist_windows": (_i, [_vp, _i, _i, _ll, _ll, _i, _i, _i, _vp, _vp, _ll, _vp]),
     "tda_corr_to_dist_f64": (_i, [_vp, _i, _i, _vp, _vp]),
     "tda_symmetrize_f64_to_f32": (_i, [_vp, _ll, _i, _vp, _vp]),
+    "tda_validate_distance_f64": (_i, [_vp, _ll, _i, _vp, _vp, _vp]),
     "tda_compute_tau": (_i, [_vp, _ll, _i, _ll, _i, _vp, _vp]),
     "tda_takens_cloud": (_i, [_vp, _ll, _i, _ll, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "tda_pairwise_dist_f32": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp]),
     "tda_wasserstein_batched": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _ll, _vp, _vp]),
+    "tda_wasserstein_batched_f64": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _ll, _vp, _vp]),
     "tda_eeg_features_host": (_i, [_vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "tda_rips_h01_large_workspace_bytes": (_sz, [_i, _i]),
     "tda_rips_h01_large": (_i, [_vp, _vp, _i, _i, _i, _ll, _f, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
@@ -42,6 +44,7 @@ SIGNATURES = {
     "tda_rips_h01_host": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i]),
     "tda_rips_h01_condensed_host": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i]),
     "tda_eeg_features_condensed_host": (_i, [_vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "tda_eeg_features_f64_host": (_i, [_vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
 }
 
 _lib = None

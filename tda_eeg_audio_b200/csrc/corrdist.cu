@@ -201,8 +201,61 @@ __global__ void symmetrize_kernel(const double* __restrict__ D, long long B, int
     v = fmax(v, 0.0);
     out[e] = (float)v;
 }
+// validate_distance_matrix (/root/reference/scripts/tda_eeg_classification_v2.py:110-140) for a batch:
+// one warp per matrix.  flags: TDA_DM_* bits; stats[b] = { max |D - D^T|, min D, max |diag| } with
+// numpy's NaN propagation (np.max / np.min return NaN as soon as one is present).
+__global__ void __launch_bounds__(128) validate_kernel(const double* __restrict__ D, long long B, int n,
+                                                       int* __restrict__ flags, double* __restrict__ stats) {
+    const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const int lane = threadIdx.x & 31;
+    const double* M = D + b * (long long)n * n;
+    int f = 0;
+    double mx_asym = 0.0, mn = __longlong_as_double(0x7FF0000000000000ll), mx_diag = 0.0;
+    bool nan_asym = false, nan_any = false, nan_diag = false;
+    for (int e = lane; e < n * n; e += 32) {
+        const int i = e / n, j = e - i * n;
+        const double a = M[e], t = M[(size_t)j * n + i];
+        // np.allclose(D, D.T, rtol=1e-5, atol=1e-8): |a - t| <= atol + rtol |t|, false for NaN
+        const double diff = fabs(a - t);
+        if (!(diff <= 1e-8 + 1e-5 * fabs(t))) f |= TDA_DM_ASYMMETRIC;
+        if (diff != diff) nan_asym = true; else mx_asym = fmax(mx_asym, diff);
+        if (a < -1e-10) f |= TDA_DM_NEGATIVE;
+        if (a != a) { f |= TDA_DM_NAN; nan_any = true; } else mn = fmin(mn, a);
+        if (isinf(a)) f |= TDA_DM_INF;
+        if (i == j) {
+            if (!(fabs(a) <= 1e-10)) f |= TDA_DM_DIAGONAL;   // np.allclose(diag, 0, atol=1e-10)
+            if (a != a) nan_diag = true; else mx_diag = fmax(mx_diag, fabs(a));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        f |= __shfl_xor_sync(0xFFFFFFFFu, f, o);
+        mx_asym = fmax(mx_asym, __shfl_xor_sync(0xFFFFFFFFu, mx_asym, o));
+        mn = fmin(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
+        mx_diag = fmax(mx_diag, __shfl_xor_sync(0xFFFFFFFFu, mx_diag, o));
+    }
+    const bool na = __any_sync(0xFFFFFFFFu, nan_asym), nn = __any_sync(0xFFFFFFFFu, nan_any),
+               nd = __any_sync(0xFFFFFFFFu, nan_diag);
+    if (lane == 0) {
+        const double qnan = __longlong_as_double(0x7FF8000000000000ll);
+        flags[b] = f;
+        stats[3 * b] = na ? qnan : mx_asym;
+        stats[3 * b + 1] = nn ? qnan : mn;
+        stats[3 * b + 2] = nd ? qnan : mx_diag;
+    }
+}
 }  // namespace corrdist
 }  // namespace tda
+
+extern "C" int tda_validate_distance_f64(const double* D, long long B, int n, int* flags, double* stats,
+                                         void* stream) {
+    if (!D || !flags || !stats || B < 0 || n < 1) return TDA_E_ARG;
+    if (B == 0) return 0;
+    tda::corrdist::validate_kernel<<<(unsigned)((B + 3) / 4), 128, 0, (cudaStream_t)stream>>>(D, B, n, flags, stats);
+    tda::count_launch();
+    return (int)cudaGetLastError();
+}
 
 extern "C" int tda_corr_to_dist_f64(const double* corr, int n, int method, double* dist, void* stream) {
     if (!corr || !dist || n < 1 || method < 0 || method > 3) return TDA_E_ARG;

@@ -28,9 +28,9 @@ namespace wasserstein {
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 constexpr double kInf = 1e300;
 
-struct Params {
-    const float* bdA; const int* nA; int nA_stride, capA, limA;
-    const float* bdB; const int* nB; int nB_stride, capB, limB;
+template <typename TIn> struct Params {
+    const TIn* bdA; const int* nA; int nA_stride, capA, limA;
+    const TIn* bdB; const int* nB; int nB_stride, capB, limB;
     const int* idxA; const int* idxB;  // optional gather indices (pair k = A[idxA[k]] vs B[idxB[k]])
     long long B;
     double* out;
@@ -49,20 +49,22 @@ __host__ __device__ inline size_t smem_bytes(int rows_cap, int cols_cap) {
 }
 
 // compact the finite rows of a diagram into (x, y) float64 pairs; empty -> one point (0,0)
-__device__ int load_diagram(const float* __restrict__ bd, int n, int cap, double* pts, int lane) {
+// (TIn = float: the Rips engines' own output, exact float32 values; TIn = double: arbitrary diagrams
+// of the drop-in call, which persim treats in float64)
+template <typename TIn>
+__device__ int load_diagram(const TIn* __restrict__ bd, int n, int cap, double* pts, int lane) {
     if (n > cap) n = cap;
     int m = 0;
-    const float2* rows = reinterpret_cast<const float2*>(bd);
     for (int k0 = 0; k0 < n; k0 += 32) {
         const int k = k0 + lane;
-        float2 r = make_float2(0.f, 0.f);
+        double2 r = make_double2(0.0, 0.0);
         bool ok = false;
-        if (k < n) { r = rows[k]; ok = isfinite(r.x) && isfinite(r.y); }
+        if (k < n) { r.x = (double)bd[2 * k]; r.y = (double)bd[2 * k + 1]; ok = isfinite(r.x) && isfinite(r.y); }
         const uint32_t bal = __ballot_sync(kFull, ok);
         if (ok) {
             const int pos = m + __popc(bal & ((1u << lane) - 1u));
-            pts[2 * pos] = (double)r.x;
-            pts[2 * pos + 1] = (double)r.y;
+            pts[2 * pos] = r.x;
+            pts[2 * pos + 1] = r.y;
         }
         m += __popc(bal);
     }
@@ -74,7 +76,8 @@ __device__ int load_diagram(const float* __restrict__ bd, int n, int cap, double
     return m;
 }
 
-__global__ void __launch_bounds__(32) wasserstein_kernel(Params p) {
+template <typename TIn>
+__global__ void __launch_bounds__(32) wasserstein_kernel(Params<TIn> p) {
     extern __shared__ __align__(16) unsigned char wsm[];
     const int lane = threadIdx.x;
     const int RC = p.rows_cap, CC = p.cols_cap;
@@ -187,14 +190,16 @@ __global__ void __launch_bounds__(32) wasserstein_kernel(Params p) {
 }  // namespace wasserstein
 }  // namespace tda
 
-extern "C" int tda_wasserstein_batched(const float* bdA, const int* nA, int nA_stride, int capA, int limA,
-                                       const float* bdB, const int* nB, int nB_stride, int capB, int limB,
-                                       const int* idxA, const int* idxB, long long B, double* out, void* stream) {
-    using namespace tda::wasserstein;
+namespace tda {
+namespace wasserstein {
+template <typename TIn>
+static int launch(const TIn* bdA, const int* nA, int nA_stride, int capA, int limA, const TIn* bdB, const int* nB,
+                  int nB_stride, int capB, int limB, const int* idxA, const int* idxB, long long B, double* out,
+                  void* stream) {
     if (!bdA || !nA || !bdB || !nB || !out || B < 0 || capA < 0 || capB < 0 || nA_stride < 1 || nB_stride < 1)
         return TDA_E_ARG;
     if (B == 0) return 0;
-    Params p;
+    Params<TIn> p;
     p.bdA = bdA; p.nA = nA; p.nA_stride = nA_stride; p.capA = capA;
     p.bdB = bdB; p.nB = nB; p.nB_stride = nB_stride; p.capB = capB;
     p.idxA = idxA; p.idxB = idxB; p.B = B; p.out = out;
@@ -207,7 +212,7 @@ extern "C" int tda_wasserstein_batched(const float* bdA, const int* nA, int nA_s
     if (p.rows_cap + p.cols_cap + 1 > 1024) return TDA_E_SIZE;
     const size_t smem = smem_bytes(p.rows_cap, p.cols_cap);
     if (smem > 227 * 1024) return TDA_E_SIZE;
-    cudaError_t e = cudaFuncSetAttribute(wasserstein_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(wasserstein_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -218,7 +223,24 @@ extern "C" int tda_wasserstein_batched(const float* bdA, const int* nA, int nA_s
     long long grid = (long long)sms * per_sm;
     if (grid > B) grid = B;
     tda::ProfScope prof("wasserstein", (cudaStream_t)stream);
-    wasserstein_kernel<<<(int)grid, 32, smem, (cudaStream_t)stream>>>(p);
+    wasserstein_kernel<TIn><<<(int)grid, 32, smem, (cudaStream_t)stream>>>(p);
     tda::count_launch();
     return (int)cudaGetLastError();
+}
+}  // namespace wasserstein
+}  // namespace tda
+
+extern "C" int tda_wasserstein_batched(const float* bdA, const int* nA, int nA_stride, int capA, int limA,
+                                       const float* bdB, const int* nB, int nB_stride, int capB, int limB,
+                                       const int* idxA, const int* idxB, long long B, double* out, void* stream) {
+    return tda::wasserstein::launch<float>(bdA, nA, nA_stride, capA, limA, bdB, nB, nB_stride, capB, limB, idxA, idxB,
+                                           B, out, stream);
+}
+
+extern "C" int tda_wasserstein_batched_f64(const double* bdA, const int* nA, int nA_stride, int capA, int limA,
+                                           const double* bdB, const int* nB, int nB_stride, int capB, int limB,
+                                           const int* idxA, const int* idxB, long long B, double* out,
+                                           void* stream) {
+    return tda::wasserstein::launch<double>(bdA, nA, nA_stride, capA, limA, bdB, nB, nB_stride, capB, limB, idxA,
+                                            idxB, B, out, stream);
 }

@@ -3,7 +3,11 @@ running every numeric stage on the GPU in one batch per call instead of a Python
 
   preprocess_file            notebooks/1_preprocesamiento.ipynb:340-436
   build_graphs_for_file      notebooks/2_graph_construction.ipynb:100-150
+  validate_distance_matrix   scripts/tda_eeg_classification_v2.py:110-140   (device-side checker)
   process_file_features      scripts/tda_eeg_classification_v2.py:338-442   (md5-seeded window choice)
+  compute_min_windows_per_band / create_dataset
+                             scripts/tda_eeg_classification_v2.py:445-474, 499-606 (a directory tree ->
+                             X, y, subjects; ONE Rips launch per band over all recordings)
   get_audio_diagrams / get_eeg_diagrams / compute_cross_wasserstein
                              scripts/matched_vs_mismatched.py:35-95
   process_recording          scripts/tda_eeg_audio_comparison.py:45-127     (linspace window choice,
@@ -19,7 +23,7 @@ import numpy as np
 from . import audio as _audio
 from . import dsp, pipeline, storage
 from .features import FEATURE_NAMES, aggregate_windows, diagram_features
-from .rips import rips_h01_batched
+from .rips import rips_h01_checked
 
 WINDOW_SEC = 1.0
 OVERLAP = 0.75
@@ -102,7 +106,52 @@ def _eeg_rips(dist_matrices, thresh, cap1=None, want_pairs=False):
     _lib.check(_lib.load().tda_symmetrize_f64_to_f32(d64.data_ptr(), B, n, d32.data_ptr(),
                                                     torch.cuda.current_stream().cuda_stream),
                "tda_symmetrize_f64_to_f32")
-    return rips_h01_batched(d32, thresh=float(thresh), cap1=cap1, want_pairs=want_pairs)
+    return rips_h01_checked(d32, thresh=float(thresh), cap1=cap1, want_pairs=want_pairs)
+
+
+# the reference's messages (tda_eeg_classification_v2.py:110-140), in its order
+def _validation_issues(flags, stats):
+    issues = []
+    if flags & 1:
+        issues.append(f"No simétrica: asimetría máxima={stats[0]:.6f}")
+    if flags & 2:
+        issues.append(f"Valores negativos presentes: min={stats[1]:.6f}")
+    if flags & 4:
+        issues.append(f"Diagonal no cero: max={stats[2]:.6f}")
+    if flags & 8:
+        issues.append("Contiene valores NaN")
+    if flags & 16:
+        issues.append("Contiene valores Inf")
+    return issues
+
+
+def validate_distance_matrices(D64):
+    """Batched checker: D64 CUDA float64 (B, n, n) -> (flags (B,) int32, stats (B, 3) float64) on the
+    device (TDA_DM_* bits of include/tda_b200.h)."""
+    import torch
+    from . import _lib
+    D64 = D64.contiguous()
+    B, n, _ = D64.shape
+    flags = torch.zeros((B,), dtype=torch.int32, device=D64.device)
+    stats = torch.zeros((B, 3), dtype=torch.float64, device=D64.device)
+    _lib.check(_lib.load().tda_validate_distance_f64(D64.data_ptr(), B, n, flags.data_ptr(), stats.data_ptr(),
+                                                    torch.cuda.current_stream().cuda_stream),
+               "tda_validate_distance_f64")
+    return flags, stats
+
+
+def validate_distance_matrix(distance_matrix, name=""):
+    """tda_eeg_classification_v2.validate_distance_matrix: (is_valid, issues) with the reference's own
+    messages; the checks themselves run on the device."""
+    distance_matrix = np.asarray(distance_matrix)
+    if distance_matrix.ndim != 2:
+        return False, [f"No es 2D: forma={distance_matrix.shape}"]
+    n, m = distance_matrix.shape
+    if n != m:
+        return False, [f"No es cuadrada: forma=({n}, {m})"]
+    flags, stats = validate_distance_matrices(_cuda(distance_matrix)[None])
+    issues = _validation_issues(int(flags[0].item()), stats[0].tolist())
+    return len(issues) == 0, issues
 
 
 def process_file_features(file_dir, freq_bands, max_dim=1, max_edge_length=2.0, max_windows_per_band=None,
@@ -122,6 +171,9 @@ def process_file_features(file_dir, freq_bands, max_dim=1, max_edge_length=2.0, 
         metadata["n_windows"][band] = n_windows
         if n_windows == 0:
             continue
+        is_valid, issues = validate_distance_matrix(dm[0], f"{band}[0]")
+        if not is_valid:
+            metadata["validation_issues"].extend([f"{band}: {i}" for i in issues])
         use = select_window_indices(file_dir.name, band, n_windows, max_windows_per_band, window_sampling,
                                     random_state)
         metadata["n_windows_used"][band] = len(use)
@@ -140,12 +192,159 @@ def process_file_features(file_dir, freq_bands, max_dim=1, max_edge_length=2.0, 
     return file_features, metadata
 
 
+def compute_min_windows_per_band(graphs_dirs, freq_bands):
+    """tda_eeg_classification_v2.py:445-474: smallest window count per band over the whole data set
+    (array headers only: np.load(mmap_mode="r"))."""
+    min_windows = {band: np.inf for band in freq_bands}
+    for graphs_dir in graphs_dirs:
+        graphs_dir = Path(graphs_dir)
+        if not graphs_dir.exists():
+            continue
+        for file_dir in (d for d in graphs_dir.iterdir() if d.is_dir()):
+            for band in freq_bands:
+                dist_file = file_dir / f"{band}_distances.npy"
+                if not dist_file.exists():
+                    continue
+                try:
+                    n_windows = np.load(dist_file, mmap_mode="r").shape[0]
+                except Exception:
+                    continue
+                if n_windows > 0:
+                    min_windows[band] = min(min_windows[band], n_windows)
+    return {band: (0 if val == np.inf else int(val)) for band, val in min_windows.items()}
+
+
+def create_dataset(graphs_dir_slow, graphs_dir_fast, freq_bands, max_dim=1, max_edge_length=2.0,
+                   equalize_windows=True, window_sampling="random", max_windows_per_band="min", random_state=42,
+                   batch_start=0, batch_end=None, verbose=True):
+    """tda_eeg_classification_v2.create_dataset (:499-606): graphs/<slow|fast>/<recording>/<band>_distances.npy
+    -> (X, y, subjects, feature_names, filenames, metadata), same entry order (sorted slow then sorted
+    fast), same window choice, same column order, same skipping of recordings without features.
+
+    Where the reference calls process_file_features per recording (a ripser call per window), all the
+    selected windows of ALL recordings of a band go through one symmetrise + Rips + feature launch; the
+    mean / std over a recording's windows is one aggregation launch per distinct window count (one,
+    when the windows are equalised)."""
+    import torch
+    graphs_dir_slow, graphs_dir_fast = Path(graphs_dir_slow), Path(graphs_dir_fast)
+    say = print if verbose else (lambda *a, **k: None)
+    if equalize_windows:
+        if max_windows_per_band == "min":
+            max_windows_per_band = compute_min_windows_per_band([graphs_dir_slow, graphs_dir_fast], freq_bands)
+            say("\nEqualizando ventanas por banda (min global):")
+            for band, nmin in max_windows_per_band.items():
+                say(f"  {band}: {nmin} ventanas")
+        else:
+            say(f"\nEqualizando ventanas por banda (máx fijo): {max_windows_per_band}")
+    slow_dirs = sorted(d for d in graphs_dir_slow.iterdir() if d.is_dir())
+    fast_dirs = sorted(d for d in graphs_dir_fast.iterdir() if d.is_dir())
+    entries = [(d, 0) for d in slow_dirs] + [(d, 1) for d in fast_dirs]
+    total_entries = len(entries)
+    if batch_end is None or batch_end < 0:
+        batch_end = total_entries
+    batch_start = max(0, batch_start)
+    batch_end = min(batch_end, total_entries)
+    entries = entries[batch_start:batch_end]
+    say(f"\nProcesando {len(entries)} archivos (batch {batch_start}:{batch_end}) de total {total_entries}...")
+
+    E = len(entries)
+    features = [dict() for _ in range(E)]
+    metas = [{"n_windows": {}, "n_windows_used": {}, "validation_issues": [], "window_sampling": window_sampling,
+              "max_windows_per_band": max_windows_per_band} for _ in range(E)]
+    failed = [False] * E
+    for band in freq_bands:
+        mats, owner, first_of = [], [], []       # selected windows of every recording, their entry, first windows
+        for k, (file_dir, _) in enumerate(entries):
+            if failed[k]:
+                continue
+            try:
+                dm = storage.load_distances(file_dir, band)
+            except Exception as exc:              # the reference: a load error is noted, the band skipped
+                metas[k]["validation_issues"].append(f"{band}: error de carga - {exc}")
+                continue
+            if dm is None:
+                metas[k]["n_windows"][band] = 0
+                continue
+            n_windows = dm.shape[0]
+            metas[k]["n_windows"][band] = n_windows
+            if n_windows == 0:
+                continue
+            try:
+                use = select_window_indices(file_dir.name, band, n_windows, max_windows_per_band, window_sampling,
+                                            random_state)
+            except Exception as exc:              # the reference: any failure drops the recording
+                say(f"Error procesando {file_dir.name}: {exc}")
+                failed[k] = True
+                continue
+            metas[k]["n_windows_used"][band] = len(use)
+            first_of.append((k, dm[0]))
+            if len(use) == 0:
+                continue
+            mats.append(dm[use])
+            owner.append((k, len(use)))
+        if first_of:
+            fl, stt = validate_distance_matrices(_cuda(np.stack([m for _, m in first_of])))
+            fl, stt = fl.tolist(), stt.tolist()
+            for (k, _), f, sv in zip(first_of, fl, stt):
+                metas[k]["validation_issues"].extend([f"{band}: {i}" for i in _validation_issues(f, sv)])
+        if not mats:
+            continue
+        r = _eeg_rips(np.concatenate(mats), max_edge_length)          # one launch for the whole band
+        f = diagram_features(r)                                       # (n_total, 2, 11) on the device
+        rows = {}
+        starts = np.concatenate([[0], np.cumsum([n for _, n in owner])])
+        for cnt in sorted({n for _, n in owner}):
+            grp = [i for i, (_, n) in enumerate(owner) if n == cnt]
+            idx = torch.from_numpy(np.concatenate([np.arange(starts[i], starts[i] + cnt) for i in grp])).cuda()
+            agg = aggregate_windows(f[idx].view(len(grp), 1, cnt, 2, 11)).cpu().numpy()      # (len(grp), 44)
+            for row, i in zip(agg, grp):
+                rows[owner[i][0]] = row
+        for k, row in rows.items():
+            for q, feat in enumerate(FEATURE_NAMES):
+                features[k][f"{band}_h0_{feat}_mean"] = row[4 * q]
+                features[k][f"{band}_h0_{feat}_std"] = row[4 * q + 1]
+                features[k][f"{band}_h1_{feat}_mean"] = row[4 * q + 2]
+                features[k][f"{band}_h1_{feat}_std"] = row[4 * q + 3]
+
+    all_features, all_labels, all_subjects, all_filenames, all_metadata = [], [], [], [], []
+    for k, (file_dir, label) in enumerate(entries):
+        if failed[k] or len(features[k]) == 0:
+            continue
+        meta = metas[k]
+        meta["n_windows_total"] = int(sum(meta["n_windows"].values()))
+        meta["n_windows_used_total"] = int(sum(meta["n_windows_used"].values()))
+        filename = file_dir.name
+        parts = filename.split("_")
+        meta["filename"], meta["subject"], meta["label"] = filename, (parts[0] if parts else filename), label
+        all_features.append(features[k])
+        all_labels.append(label)
+        all_subjects.append(meta["subject"])
+        all_filenames.append(filename)
+        all_metadata.append(meta)
+    # pd.DataFrame(list of dicts): columns in order of first appearance, missing entries NaN
+    feature_names = []
+    for fd in all_features:
+        for name in fd:
+            if name not in feature_names:
+                feature_names.append(name)
+    X = np.array([[fd.get(name, np.nan) for name in feature_names] for fd in all_features], dtype=np.float64) \
+        if all_features else np.zeros((0, 0))
+    y = np.array(all_labels)
+    subjects = np.array(all_subjects)
+    say("Resumen del Dataset")
+    say("-" * 60)
+    say(f"Total de muestras: {X.shape[0]}")
+    say(f"Total de características: {X.shape[1] if X.ndim == 2 else 0}")
+    return X, y, subjects, feature_names, all_filenames, all_metadata
+
+
 # ------------------------------------------------------------------------------------------ EEG-audio
 def _diagram_lists(r, max_dim=1):
     """padded diagram tensors -> list (per item) of [H0 (k,2), H1 (k,2)] float64 arrays"""
     cnt = r["counts"].cpu().numpy()
     bd0, bd1 = r["bd0"].double().cpu().numpy(), r["bd1"].double().cpu().numpy()
-    return [[bd0[i, :cnt[i, 0]], bd1[i, :min(cnt[i, 1], bd1.shape[1])]][: max_dim + 1] for i in range(len(cnt))]
+    assert (cnt[:, 1] <= bd1.shape[1]).all(), "truncated H1 diagrams (use rips_h01_checked)"
+    return [[bd0[i, :cnt[i, 0]], bd1[i, :cnt[i, 1]]][: max_dim + 1] for i in range(len(cnt))]
 
 
 def _audio_band_diagrams(envelope, want_tensors=False):

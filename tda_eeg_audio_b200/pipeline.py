@@ -5,26 +5,33 @@ eeg_features_from_distances = process_file_features
 from __future__ import annotations
 
 from . import features as _features
-from .rips import rips_h01_batched
+from .rips import rips_h01_batched, rips_h01_checked
 
 
-def eeg_features_from_distances(D, thresh=2.0, cap1=128, state=None, want_pairs=False, n_points=None):
+def eeg_features_from_distances(D, thresh=2.0, cap1=128, state=None, want_pairs=False, n_points=None, check=True):
     """D: CUDA float32 (R, Bd, Wn, N, N), or with `n_points=N` the condensed (R, Bd, Wn, N(N-1)/2)
     of rips.condense.  Returns dict with
     table (R, Bd*44) float64, feats (R, Bd, Wn, 2, 11) float64 and the raw diagram tensors.
-    `state` (a dict) keeps every buffer alive between calls so a steady-state step allocates nothing."""
+    `state` (a dict) keeps every buffer alive between calls so a steady-state step allocates nothing.
+    `cap1` is the INITIAL row capacity of the H1 output: with `check` (default; one device->host sync
+    per call) a batch holding a window with more bars is run again with the capacity it needs (kept in
+    `state` for the following calls), and an exhausted engine capacity raises TdaError -- features are
+    never computed on truncated diagrams.  check=False leaves the status bits to the caller."""
     import torch
     R, Bd, Wn = D.shape[:3]
     B = R * Bd * Wn
     if state is None:
         state = {}
+    cap1 = max(cap1, state.get("cap1", 0))
+    run = rips_h01_checked if check else rips_h01_batched
     if n_points is None:
         N = D.shape[3]
-        rips = rips_h01_batched(D.reshape(B, N, N), thresh=thresh, cap1=cap1, want_pairs=want_pairs,
-                                out=state.setdefault("rips", {}))
+        rips = run(D.reshape(B, N, N), thresh=thresh, cap1=cap1, want_pairs=want_pairs,
+                   out=state.setdefault("rips", {}))
     else:
-        rips = rips_h01_batched(D.reshape(B, D.shape[3]), thresh=thresh, cap1=cap1, want_pairs=want_pairs,
-                                out=state.setdefault("rips", {}), n_points=n_points)
+        rips = run(D.reshape(B, D.shape[3]), thresh=thresh, cap1=cap1, want_pairs=want_pairs,
+                   out=state.setdefault("rips", {}), n_points=n_points)
+    state["cap1"] = rips["bd1"].shape[1]
     feats = state.get("feats")
     if feats is None or feats.shape[0] != B:
         feats = state["feats"] = torch.empty((B, 2, 11), dtype=torch.float64, device=D.device)
@@ -32,11 +39,6 @@ def eeg_features_from_distances(D, thresh=2.0, cap1=128, state=None, want_pairs=
     table = _features.aggregate_windows(feats.view(R, Bd, Wn, 2, 11), out=state.get("table"))
     state["table"] = table
     return {"table": table, "feats": feats.view(R, Bd, Wn, 2, 11), "rips": rips, "state": state}
-
-
-def check_truncation(result):
-    """True if any window had more H1 bars than cap1 (one device->host sync)."""
-    return bool((result["rips"]["status"] & 1).any().item())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -65,7 +67,7 @@ def audio_diagrams_from_envelope(env, fs=250, bands=None, window_sec=1.0, overla
     import numpy as np
     import torch
     from . import dsp, takens
-    from .rips import rips_h01_batched
+    from .rips import rips_h01_checked
     bands = bands or dsp.FREQ_BANDS
     names = list(bands)
     R, T = env.shape
@@ -90,7 +92,7 @@ def audio_diagrams_from_envelope(env, fs=250, bands=None, window_sec=1.0, overla
     nmax = int(npts.max().item()) if npts.numel() else 0
     nmax = max(nmax, 2)
     D = takens.pairwise_distance_f32(pts[:, :nmax].contiguous(), npts, ld=nmax)
-    rips = rips_h01_batched(D, thresh=thresh, cap1=cap1, want_pairs=want_pairs, npts=npts, engine="auto")
+    rips = rips_h01_checked(D, thresh=thresh, cap1=cap1, want_pairs=want_pairs, npts=npts, engine="auto")
     return {"rips": rips, "tau": tau.view(R, nb), "idx": idx, "npts": npts, "shape": (R, nb, n_sel), "D": D}
 
 

@@ -112,6 +112,53 @@ def rips_h01_batched(D, thresh=float("inf"), cap1=None, want_pairs=True, out=Non
     return out
 
 
+ST_H1_TRUNCATED, ST_NAN_INPUT, ST_INTERNAL = 1, 2, 4   # include/tda_b200.h: TDA_ST_*
+
+
+def rips_h01_checked(D, thresh=float("inf"), cap1=None, out=None, **kw):
+    """rips_h01_batched, then the per-item status reduced on the host (one device->host sync):
+
+      * TDA_ST_INTERNAL (an engine capacity exhausted; the item's diagrams are NOT valid) raises TdaError;
+      * TDA_ST_H1_TRUNCATED (more H1 bars than `cap1` rows): the batch is run again with cap1 = the
+        largest true count -- ripser never truncates, so neither do the drop-ins and drivers;
+      * TDA_ST_NAN_INPUT (NaN distances: those edges are absent, ripser's own comparison semantics)
+        warns once per call.
+    Returns the same dict (with the enlarged bd1 / pr1 after a re-run)."""
+    import torch
+    import warnings
+    out = rips_h01_batched(D, thresh=thresh, cap1=cap1, out=out, **kw)
+    st = out["status"]
+    if st.numel() == 0 or not bool((st != 0).any().item()):
+        return out
+    flags = 0
+    for v in torch.unique(st).tolist():
+        flags |= int(v)
+    if flags & ST_INTERNAL:
+        bad = torch.nonzero(st & ST_INTERNAL).flatten()[:8].tolist()
+        raise _lib.TdaError(f"rips_h01_batched: internal capacity exhausted (TDA_ST_INTERNAL) for items {bad}: "
+                            "more simultaneously alive H1 classes than the last tier holds")
+    if flags & ST_NAN_INPUT:
+        warnings.warn("rips_h01_batched: NaN distances in the input; those edges were left out "
+                      "(TDA_ST_NAN_INPUT)", RuntimeWarning, stacklevel=2)
+    if flags & ST_H1_TRUNCATED:
+        need = int(out["counts"][:, 1].max().item())
+        out = rips_h01_batched(D, thresh=thresh, cap1=need, out=out, **kw)
+        assert not bool((out["status"] & ST_H1_TRUNCATED).any().item())
+    return out
+
+
+def tier_counts(out, n_points):
+    """How many windows of the last rips_h01_batched call on `out` (N <= 64 engine) each capacity
+    tier finished: dict W -> count for the 1 / 2 / 4 / 64-word tiers (the one-word tier exists for
+    47-point windows only).  Reads the hand-over counters the tiers leave at the head of the
+    workspace (csrc/rips_small.cu: counters[2] -> two-word tier, [0] -> four-word, [1] -> 64-word);
+    one device->host sync."""
+    B = int(out["counts"].shape[0])
+    c = out["ws"][:12].view(__import__("torch").int32).tolist()
+    to_w2, to_w4, to_w64 = (c[2] if n_points == 47 else B), c[0], c[1]
+    return {1: B - to_w2, 2: to_w2 - to_w4, 4: to_w4 - to_w64, 64: to_w64}
+
+
 def ripser(X, maxdim=1, thresh=np.inf, coeff=2, distance_matrix=False, do_cocycles=False,
            metric="euclidean", n_perm=None):
     """Single-matrix drop-in for ripser.ripser (maxdim<=1, coeff=2 — all the reference uses).
@@ -129,7 +176,7 @@ def ripser(X, maxdim=1, thresh=np.inf, coeff=2, distance_matrix=False, do_cocycl
     else:
         from .takens import pairwise_distance_f32  # device Gram-trick distance, f64 -> f32
         dm = pairwise_distance_f32(torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).cuda()[None])[0]
-    r = rips_h01_batched(dm[None], thresh=float(thresh))
+    r = rips_h01_checked(dm[None], thresh=float(thresh))
     n0, n1 = (int(x) for x in r["counts"][0].tolist())
     dg0 = r["bd0"][0, :n0].double().cpu().numpy().reshape(-1, 2)
     dg1 = r["bd1"][0, :n1].double().cpu().numpy().reshape(-1, 2)

@@ -28,7 +28,7 @@ def compute_audio_persistence(point_cloud, max_dim=MAX_DIM, max_edge_length=MAX_
     """utils.py:123-132 — min-max normalise the cloud, then ripser(pc, maxdim, thresh)."""
     import torch
     from . import takens as _t
-    from .rips import rips_h01_batched
+    from .rips import rips_h01_checked
     point_cloud = np.asarray(point_cloud, dtype=np.float64)
     if len(point_cloud) < 3:
         return [np.array([[0, 0]]), np.array([[0, 0]])]
@@ -38,7 +38,7 @@ def compute_audio_persistence(point_cloud, max_dim=MAX_DIM, max_edge_length=MAX_
     rg[rg == 0] = 1
     pcn = ((pc - mn) / rg)[None]
     D = _t.pairwise_distance_f32(pcn)
-    r = rips_h01_batched(D, thresh=float(max_edge_length))
+    r = rips_h01_checked(D, thresh=float(max_edge_length))
     n0, n1 = (int(x) for x in r["counts"][0].tolist())
     dg = [r["bd0"][0, :n0].double().cpu().numpy().reshape(-1, 2)]
     if max_dim >= 1:
@@ -51,7 +51,7 @@ def compute_eeg_persistence(dist_matrix, max_dim=MAX_DIM, max_edge_length=MAX_ED
     ripser(dm, maxdim, thresh, distance_matrix=True)."""
     import torch
     from . import _lib
-    from .rips import rips_h01_batched
+    from .rips import rips_h01_checked
     dm = np.ascontiguousarray(dist_matrix, dtype=np.float64)
     if dm.ndim != 2 or dm.shape[0] != dm.shape[1]:
         raise Exception("Distance matrix is not square")
@@ -61,7 +61,7 @@ def compute_eeg_persistence(dist_matrix, max_dim=MAX_DIM, max_edge_length=MAX_ED
     _lib.check(_lib.load().tda_symmetrize_f64_to_f32(d64.data_ptr(), 1, n, d32.data_ptr(),
                                                     torch.cuda.current_stream().cuda_stream),
                "tda_symmetrize_f64_to_f32")
-    r = rips_h01_batched(d32, thresh=float(max_edge_length))
+    r = rips_h01_checked(d32, thresh=float(max_edge_length))
     n0, n1 = (int(x) for x in r["counts"][0].tolist())
     dg = [r["bd0"][0, :n0].double().cpu().numpy().reshape(-1, 2)]
     if max_dim >= 1:

@@ -213,3 +213,60 @@ def notebooks_golden():
 
 if __name__ == "__main__":
     notebooks_golden()
+
+
+def dataset_golden():
+    """create_dataset / compute_min_windows_per_band / validate_distance_matrix of the reference
+    (tda_eeg_classification_v2.py:110-140, 445-474, 499-606), executed where they lie on
+    tests.inputs.small_graph_dataset with ripser replaced by the CPU oracle -> dataset.json."""
+    import hashlib
+    import io
+    import json
+    import tempfile
+    from contextlib import redirect_stdout
+    from pathlib import Path
+    import pandas as pd
+    from oracle import rips as orips
+    u = reference_import.load_utils()
+    ns = {"np": np, "pd": pd, "hashlib": hashlib, "ripser": orips.ripser, "N_JOBS": 1,
+          "tqdm": lambda it, **kw: it}
+    _reference_functions("tda_eeg_classification_v2.py",
+                         ["create_dataset", "compute_min_windows_per_band", "process_file_features",
+                          "compute_persistence_diagram", "extract_persistence_features", "validate_distance_matrix"], ns)
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        slow, fast = inputs.small_graph_dataset(td)
+        out["min_windows"] = ns["compute_min_windows_per_band"]([slow, fast], u.FREQ_BANDS)
+        for tag, kw in (("min_random", {}),
+                        ("all_windows", {"equalize_windows": False, "max_windows_per_band": None}),
+                        ("fixed12_first_batch1to4", {"max_windows_per_band": 12, "window_sampling": "first",
+                                                     "batch_start": 1, "batch_end": 4})):
+            with redirect_stdout(io.StringIO()):
+                X, y, subjects, names, filenames, meta = ns["create_dataset"](slow, fast, u.FREQ_BANDS, **kw)
+            out[tag] = {"X": [[None if v != v else float(v) for v in row] for row in X], "y": [int(v) for v in y],
+                        "subjects": list(map(str, subjects)), "feature_names": names, "filenames": filenames,
+                        "n_windows_used": [m["n_windows_used"] for m in meta],
+                        "validation_issues": [m["validation_issues"] for m in meta]}
+    # the input checker on its own
+    rng = np.random.default_rng(5)
+    D = inputs.eeg_like(rng, 1)[0].astype(np.float64)
+    cases = {"ok": D.copy()}
+    c = D.copy(); c[2, 5] += 1e-3; cases["asymmetric"] = c
+    c = D.copy(); c[1, 4] = c[4, 1] = -0.25; cases["negative"] = c
+    c = D.copy(); c[6, 6] = 1e-3; cases["diagonal"] = c
+    c = D.copy(); c[0, 9] = c[9, 0] = np.nan; cases["nan"] = c
+    c = D.copy(); c[3, 8] = c[8, 3] = np.inf; cases["inf"] = c
+    c = D.copy(); c[0, 1] = np.nan; c[5, 5] = np.nan; c[7, 2] = -np.inf; cases["everything"] = c
+    out["validate"] = {}
+    for k, m in cases.items():
+        ok, issues = ns["validate_distance_matrix"](m, k)
+        out["validate"][k] = {"valid": bool(ok), "issues": issues}
+    out["validate"]["not_square"] = dict(zip(("valid", "issues"), ns["validate_distance_matrix"](np.zeros((3, 4)))))
+    out["validate"]["not_2d"] = dict(zip(("valid", "issues"), ns["validate_distance_matrix"](np.zeros((3,)))))
+    json.dump(out, open(os.path.join(HERE, "dataset.json"), "w"), indent=1, sort_keys=True, ensure_ascii=False)
+    print("dataset.json:", {k: (len(v["X"]), len(v["feature_names"])) for k, v in out.items() if isinstance(v, dict) and "X" in v},
+          out["min_windows"])
+
+
+if __name__ == "__main__":
+    dataset_golden()

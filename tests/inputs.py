@@ -70,6 +70,36 @@ def tiny_dataset(root, seed=5, seconds=8):
     return mat, gdir
 
 
+def small_graph_dataset(root, seed=11):
+    """graphs/<slow|fast>/<recording>/<band>_distances.npy for five recordings of different lengths
+    (6-9 s: 21 to 33 windows at 75 % overlap) in the reference's layout, written with the scipy
+    restatement of notebooks 1-2; one recording lacks the gamma band, one band file holds a slightly
+    asymmetric first matrix (so the input checker has something to report).  Input of create_dataset:
+    tests/golden/make_golden.py::dataset_golden runs the reference's own function on it."""
+    from pathlib import Path
+    from oracle import signal_ref
+    root = Path(root)
+    rng = np.random.default_rng(seed)
+    spec = [("slow", "S01_trial1", 6), ("slow", "S02_trial4", 8), ("slow", "S02_trial9", 7),
+            ("fast", "S01_trial2", 9), ("fast", "S03_trial1", 6)]
+    for cond, name, seconds in spec:
+        n = 250 * seconds
+        A = rng.standard_normal((47, 8)) / np.sqrt(8)
+        eeg = A @ rng.standard_normal((8, n)) + 0.5 * rng.standard_normal((47, n))
+        gdir = root / "graphs" / cond / name
+        gdir.mkdir(parents=True, exist_ok=True)
+        for band, (lo, hi) in signal_ref.FREQ_BANDS.items():
+            if name == "S03_trial1" and band == "gamma":
+                continue
+            filt = signal_ref.apply_bandpass_filter(eeg, lo, hi, 250)
+            wins, _ = signal_ref.create_sliding_windows(filt, 1.0, 0.75, 250)
+            dist = np.stack([signal_ref.correlation_to_distance(signal_ref.compute_correlation_matrix(w)) for w in wins])
+            if name == "S02_trial4" and band == "theta":
+                dist[0, 3, 7] += 1e-3
+            np.save(gdir / f"{band}_distances.npy", dist)
+    return root / "graphs" / "slow", root / "graphs" / "fast"
+
+
 # ------------------------------------------------------------------------------------------------
 # Known answers from theory (no code of ours, no third-party library involved)
 # ------------------------------------------------------------------------------------------------

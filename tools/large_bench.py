@@ -1,6 +1,5 @@
 """Throughput of the Rips engines on Takens clouds: the
-grid-cooperative engine (rips_large) at N = 1000/1500/2000 and against rips_medium at the audio
-sizes.  Device-resident distance matrices, CUDA events.  One JSON line per case."""
+grid-cooperative engine (rips_large) at N = 1000/1500/2000 and at the audio sizes.  Device-resident distance matrices, CUDA events.  One JSON line per case."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -40,8 +39,7 @@ def timed(fn, n=3, warm=1):
 
 
 CASES = [("large", 64, 1000, 2.0), ("large", 64, 1500, 2.0), ("large", 64, 2000, 2.0), ("large", 64, 2000, 0.25),
-         ("large", 296, 1000, 2.0), ("large", 8192, 124, 2.0), ("medium", 8192, 124, 2.0), ("large", 8192, 248, 2.0),
-         ("medium", 8192, 248, 2.0)]
+         ("large", 296, 1000, 2.0), ("large", 8192, 124, 2.0), ("large", 8192, 248, 2.0)]
 
 
 def main():
