@@ -216,9 +216,11 @@ __global__ void __launch_bounds__(128) validate_kernel(const double* __restrict_
     for (int e = lane; e < n * n; e += 32) {
         const int i = e / n, j = e - i * n;
         const double a = M[e], t = M[(size_t)j * n + i];
-        // np.allclose(D, D.T, rtol=1e-5, atol=1e-8): |a - t| <= atol + rtol |t|, false for NaN
+        // np.allclose(D, D.T, rtol=1e-5, atol=1e-8): finite pairs |a - t| <= atol + rtol |t|, non-finite
+        // ones must be equal (inf == inf is close, NaN never is)
         const double diff = fabs(a - t);
-        if (!(diff <= 1e-8 + 1e-5 * fabs(t))) f |= TDA_DM_ASYMMETRIC;
+        const bool fin = isfinite(a) && isfinite(t);
+        if (!(fin ? diff <= 1e-8 + 1e-5 * fabs(t) : a == t)) f |= TDA_DM_ASYMMETRIC;
         if (diff != diff) nan_asym = true; else mx_asym = fmax(mx_asym, diff);
         if (a < -1e-10) f |= TDA_DM_NEGATIVE;
         if (a != a) { f |= TDA_DM_NAN; nan_any = true; } else mn = fmin(mn, a);
