@@ -4,18 +4,27 @@
 // takes; measured 2.1x the register-tile FMA kernel of corrdist.cu with bit-identical distances and
 // correlations (profiles/r02_staged_ab.jsonl).
 //
-// Same interface, same load / centring / epilogue arithmetic as corrdist_kernel (corrdist.cu), which
-// it replaces per window for:
+// Same interface and epilogue arithmetic as corrdist_kernel (corrdist.cu), which it replaces per window for:
 //   create_sliding_windows      /root/reference/notebooks/1_preprocesamiento.ipynb:314-364 (slicing only)
 //   compute_correlation_matrix  /root/reference/notebooks/2_graph_construction.ipynb:86-97
 //   correlation_to_distance     /root/reference/notebooks/2_graph_construction.ipynb:100-122
 //
-// Why: the first generation feeds 4x4 register tiles of DFMA from shared memory, 8 LDS.64 per 16
-// DFMA, with 78 of 128 threads busy and one CTA of four warps per SM (the window takes 115 KB): 17 %
-// of the FP64 pipe.  Here a CTA of eight warps owns a window, the Gram/covariance block reuses the
-// window's shared memory (97 KB -> two CTAs = sixteen warps per SM), and every warp runs up to three
-// upper-triangular 8x8 tiles at once: per k-step of 4 samples two conflict-free LDS.64 and one DMMA
-// (256 FMAs) per tile, three independent accumulator chains.  1,323 DMMAs per 47-channel window.
+// Two persistent CTAs of eight warps per SM, each with ONE window buffer (47 rows of 250 float64 = 94 KB)
+// that the TMA engine fills: lane 0 of every warp issues a bulk asynchronous copy per channel row
+// (cp.async.bulk.shared::cluster.global, 2,000 contiguous bytes each) that completes on an mbarrier.
+// The copies of window k+1 are issued as soon as the tensor-pipe phase has read window k -- the
+// covariance block lives in its own 10.5 KB (upper-triangular tiles, packed) -- so they stream in under
+// the float64 divisions / square roots of the epilogue, and the two CTAs of an SM drift into
+// complementary phases: one multiplies while the other centres, finishes or waits for HBM.  (A single
+// double-buffered CTA of sixteen warps ran every warp through the same phase at the same time and left
+// the tensor pipe idle two thirds of the time: profiles/r02c_corrdist_ncu.json.)  Per window: centring
+// in place (a warp takes its rows four at a time), the 21 upper-triangular 8x8 tiles of X X^T with
+// mma.sync.m8n8k4.f64, three tiles in flight per warp (per k-step of 4 samples two conflict-free
+// LDS.64 and one DMMA per tile; 1,323 DMMAs per 47-channel window), and the epilogue over the 1,128
+// pairs i <= j (a cyclic folding of the matrix gives every thread real pairs, three at a time: no
+// half-idle warps in front of the divisions).
+// Shapes the bulk copies cannot take (rows not 16-byte aligned, more than one round of tiles, windows
+// beyond the shared memory) are served by corrdist_kernel.
 //
 // Fragment layout of mma.m8n8k4.f64 (PTX ISA; CuTe SM80_8x8x4_F64F64F64F64_TN, layouts SM80_8x4 /
 // SM80_8x8_Row): g = lane >> 2, t = lane & 3.  A (8x4, row): a = A[g][t].  B (4x8, col): b = B[t][g].
@@ -37,7 +46,7 @@ namespace corrdist {
 
 constexpr int kMmaThreads = 256;
 constexpr int kMmaWarps = kMmaThreads / 32;
-constexpr int kIlp = 3;   // tiles a warp keeps in flight
+constexpr int kIlp = 3;                     // tiles a warp keeps in flight
 
 __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
@@ -45,8 +54,33 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
                  : "d"(a), "d"(b));
 }
 
+// ---- mbarrier / bulk-copy primitives (PTX; the async proxy writes shared memory, the barrier counts bytes)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // row stride of the staged window in doubles: a multiple of 4 that is 4 mod 8, so that the eight
 // rows x four columns a fragment load touches fall on sixteen distinct 8-byte bank pairs per half-warp
+// (and every row starts 16-byte aligned, as the bulk copies need)
 __host__ __device__ inline int mma_ldw(int win) {
     int l = (win + 3) & ~3;
     if ((l & 7) != 4) l += 4;
@@ -60,148 +94,247 @@ corrdist_mma_kernel(const double* __restrict__ x, int R, int C, long long T, lon
     const int Cp = (C + 7) & ~7;        // channels padded to the 8x8 tile
     const int Kp = (win + 3) & ~3;      // samples padded to the k-step (zeros)
     const int ldw = mma_ldw(win);
-    double* xs = sm;                    // Cp x ldw, later overlaid by cs
-    double* cs = sm;                    // Cp x Cp covariance (written after the last read of xs)
-    double* sd = sm + (size_t)Cp * ldw; // Cp
+    const int nt = Cp / 8;
+    const int ntiles = nt * (nt + 1) / 2;          // <= kMmaWarps * kIlp (checked by the launcher)
+    double* xs = sm;                               // the window, Cp x ldw
+    double* cs = sm + (size_t)Cp * ldw;            // covariance, upper-triangular 8x8 tiles packed: ntiles x 64
+    double* sd = cs + (size_t)ntiles * 64;         // Cp
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sd + Cp);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;
-    const int nt = Cp / 8;
-    const int ntiles = nt * (nt + 1) / 2;
+    const long long items = (long long)R * W;
+    const uint32_t row_bytes = (uint32_t)win * 8u;
 
-    for (long long item = blockIdx.x; item < (long long)R * W; item += gridDim.x) {
-        const long long rec = item / W;
-        const int w = (int)(item % W);
-        const double* src = x + rec * strideR + (long long)w * step;
-        // ---- load (coalesced along time) and centre each channel: the arithmetic of corrdist_kernel
-        for (int c = warp; c < Cp; c += kMmaWarps) {
-            double* row = xs + (size_t)c * ldw;
-            if (c < C) {
-                const double* gsrc = src + (long long)c * T;
-                double s = 0;
-                for (int k = lane; k < win; k += 32) { double v = gsrc[k]; row[k] = v; s += v; }
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // the padding the copies never touch: channel rows C..Cp-1 (whole rows)
+    for (int q = tid; q < (Cp - C) * ldw; q += kMmaThreads) xs[(size_t)C * ldw + q] = 0.0;
+    fence_proxy_async();
+    __syncthreads();
+
+    // lane 0 of every warp issues the bulk copies of its rows (warp, warp + 8, ...): a bulk copy is a
+    // warp-level instruction, and 47 of them from one thread delay that thread's warp -- and with it the
+    // next barrier -- by several thousand cycles.  Thread 0 arms the barrier with the byte count; its
+    // arrival is the only pending one, so the phase cannot complete before it.
+    auto issue = [&](long long item) {
+        if (lane != 0) return;
+        const long long rec_i = item / W;
+        const int w_i = (int)(item - rec_i * W);
+        const double* src = x + rec_i * strideR + (long long)w_i * step;
+        if (warp == 0) mbar_expect_tx(bar, row_bytes * (uint32_t)C);
+        for (int c = warp; c < C; c += kMmaWarps) bulk_g2s(xs + (size_t)c * ldw, src + (long long)c * T, row_bytes, bar);
+    };
+    if ((long long)blockIdx.x < items) issue(blockIdx.x);
+
+    // tile assignment of this warp (fixed for the whole kernel)
+    int tile_i[kIlp], tile_j[kIlp], tile_l[kIlp];
 #pragma unroll
-                for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-                const double mean = s / win;
-                for (int k = lane; k < win; k += 32) row[k] -= mean;
-                for (int k = win + lane; k < Kp; k += 32) row[k] = 0.0;
-            } else {
-                for (int k = lane; k < Kp; k += 32) row[k] = 0.0;
+    for (int u = 0; u < kIlp; ++u) {
+        const int tl = u * kMmaWarps + warp;
+        int ti = 0, rem = tl < ntiles ? tl : 0;
+        while (rem >= nt - ti) { rem -= nt - ti; ++ti; }
+        tile_i[u] = tl < ntiles ? ti : -1;
+        tile_j[u] = ti + rem;
+        tile_l[u] = tl;
+    }
+    const int half = C / 2 + 1;                    // cyclic folding: offsets 0 .. floor(C/2)
+    const int npairs = C * half;
+    const float inv_half = 1.0f / (float)half;
+    constexpr int kRowsPerWarp = 8;                // rows a warp centres (C <= 64), four at a time
+    constexpr int kPairsPerThread = 3;             // pairs a thread finishes at once
+
+    // (recording, window) of the current item, advanced without a division per window
+    long long rec = (long long)blockIdx.x / W;
+    int w = (int)((long long)blockIdx.x - rec * W);
+    const long long step_rec = (long long)gridDim.x / W;
+    const int step_w = (int)((long long)gridDim.x - step_rec * W);
+    int it = 0;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+        mbar_wait(bar, (uint32_t)(it & 1));
+        // ---- centre each channel (a warp takes its rows four at a time: independent chains), zero the k-padding
+        const int nfull = win >> 5, tail = win & 31;   // whole 32-sample steps, then a partial one
+#pragma unroll
+        for (int q0 = 0; q0 < kRowsPerWarp; q0 += 4) {
+            if (warp + kMmaWarps * q0 >= C) break;
+            double* rp[4];
+            double s[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = warp + kMmaWarps * (q0 + q);
+                rp[q] = xs + (size_t)(c < C ? c : 0) * ldw + lane;
+                s[q] = 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (warp + kMmaWarps * (q0 + q) < C) {
+                    const double* p = rp[q];
+#pragma unroll 4
+                    for (int i = 0; i < nfull; ++i) s[q] += p[32 * i];
+                    if (lane < tail) s[q] += p[32 * nfull];
+                }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) s[q] += __shfl_xor_sync(0xFFFFFFFFu, s[q], o);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s[q] = s[q] / win;          // the mean, numpy's division
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (warp + kMmaWarps * (q0 + q) < C) {
+                    double* p = rp[q];
+#pragma unroll 4
+                    for (int i = 0; i < nfull; ++i) p[32 * i] -= s[q];
+                    if (lane < tail) p[32 * nfull] -= s[q];
+                    else if (32 * nfull + lane < Kp) p[32 * nfull] = 0.0;
+                }
             }
         }
         __syncthreads();
         // ---- upper-triangular 8x8 tiles of X X^T on the FP64 tensor pipe, kIlp tiles per warp at once
         double acc[kIlp][2];
-        int tile_i[kIlp], tile_j[kIlp];
-        const int rounds = (ntiles + kMmaWarps * kIlp - 1) / (kMmaWarps * kIlp);
-        // (one round for 47 channels: 21 tiles over 8 warps x 3; the accumulators of a round are
-        //  parked in registers until xs may be overwritten, so more than one round needs cs elsewhere)
-        for (int rd = 0; rd < rounds; ++rd) {
+        {
             const double* pa[kIlp];
             const double* pb[kIlp];
 #pragma unroll
             for (int u = 0; u < kIlp; ++u) {
-                const int tl = (rd * kIlp + u) * kMmaWarps + warp;
-                int ti = 0, rem = tl < ntiles ? tl : 0;
-                while (rem >= nt - ti) { rem -= nt - ti; ++ti; }
-                tile_i[u] = tl < ntiles ? ti : -1;
-                tile_j[u] = ti + rem;
+                const int ti = tile_i[u] < 0 ? 0 : tile_i[u], tj = tile_i[u] < 0 ? 0 : tile_j[u];
                 pa[u] = xs + (size_t)(ti * 8 + g) * ldw + t4;
-                pb[u] = xs + (size_t)((ti + rem) * 8 + g) * ldw + t4;
+                pb[u] = xs + (size_t)(tj * 8 + g) * ldw + t4;
                 acc[u][0] = 0.0;
                 acc[u][1] = 0.0;
             }
-            for (int k0 = 0; k0 < Kp; k0 += 4) {
+            // (warp-uniform: the 21 tiles of a 47-channel window give five warps three tiles and three warps two)
+            if (tile_i[kIlp - 1] >= 0) {
+#pragma unroll 4
+                for (int k0 = 0; k0 < Kp; k0 += 4) {
 #pragma unroll
-                for (int u = 0; u < kIlp; ++u) {
-                    if (tile_i[u] >= 0) dmma_8x8x4(acc[u][0], acc[u][1], pa[u][k0], pb[u][k0]);   // warp-uniform
+                    for (int u = 0; u < kIlp; ++u) dmma_8x8x4(acc[u][0], acc[u][1], pa[u][k0], pb[u][k0]);
                 }
-            }
-            if (rounds > 1) {
-                // general shapes: the covariance block lives behind the window instead of over it
-                double* cs2 = sd + Cp;
-                const double inv = 1.0 / (double)(win - 1);
+            } else if (tile_i[kIlp - 2] >= 0) {
+#pragma unroll 4
+                for (int k0 = 0; k0 < Kp; k0 += 4) {
 #pragma unroll
-                for (int u = 0; u < kIlp; ++u) {
-                    if (tile_i[u] >= 0) {
-                        double* o = cs2 + (size_t)(tile_i[u] * 8 + g) * Cp + tile_j[u] * 8 + 2 * t4;
-                        o[0] = acc[u][0] * inv;
-                        o[1] = acc[u][1] * inv;
-                    }
+                    for (int u = 0; u < kIlp - 1; ++u) dmma_8x8x4(acc[u][0], acc[u][1], pa[u][k0], pb[u][k0]);
                 }
+            } else if (tile_i[0] >= 0) {
+#pragma unroll 4
+                for (int k0 = 0; k0 < Kp; k0 += 4) dmma_8x8x4(acc[0][0], acc[0][1], pa[0][k0], pb[0][k0]);
             }
         }
-        __syncthreads();   // every warp has finished reading xs
-        if (rounds == 1) {
+        // ---- covariance tiles (their own region: the window buffer is free as soon as every warp has
+        //      finished reading it, and the next window's rows start streaming in under the epilogue)
+        {
             const double inv = 1.0 / (double)(win - 1);
 #pragma unroll
             for (int u = 0; u < kIlp; ++u) {
                 if (tile_i[u] >= 0) {
-                    double* o = cs + (size_t)(tile_i[u] * 8 + g) * Cp + tile_j[u] * 8 + 2 * t4;
+                    double* o = cs + (size_t)tile_l[u] * 64 + g * 8 + 2 * t4;
                     o[0] = acc[u][0] * inv;
                     o[1] = acc[u][1] * inv;
                 }
             }
         }
-        const double* cov = rounds == 1 ? cs : sd + Cp;
+        fence_proxy_async();   // generic-proxy writes to the window (centring) before the bulk copies that refill it
         __syncthreads();
-        // sd must not alias cov: for rounds == 1 it sits behind the window, for rounds > 1 in front of cs2
-        for (int c = tid; c < C; c += kMmaThreads) sd[c] = sqrt(cov[(size_t)c * Cp + c]);
+        if (item + gridDim.x < items) issue(item + gridDim.x);
+        for (int c = tid; c < C; c += kMmaThreads) {
+            const int tc = c >> 3;
+            sd[c] = sqrt(cs[(size_t)(tc * nt - tc * (tc - 1) / 2) * 64 + (c & 7) * 9]);
+        }
         __syncthreads();
-        // ---- epilogue over i <= j: the arithmetic of corrdist_kernel
+        // ---- epilogue over the pairs i <= j: pair (r, (r + o) mod C), o = 0 .. floor(C/2); a thread works
+        //      on kPairsPerThread pairs at once (independent division / square-root chains)
         const long long oo = rec * strideO + (long long)w * C * C;
         float* Dw = D ? D + oo : nullptr;
         double* Cw = corr ? corr + oo : nullptr;
-        for (int e = tid; e < C * C; e += kMmaThreads) {
-            const int i = e / C, j = e % C;
-            if (i > j) continue;
-            double r = cov[(size_t)i * Cp + j];
-            r = r / sd[i];
-            r = r / sd[j];                       // numpy: c /= stddev[:, None]; c /= stddev[None, :]
-            if (r != r) r = 0.0;                 // nan_to_num(nan=0.0): zero-variance channel
-            else r = fmin(fmax(r, -1.0), 1.0);   // np.clip inside corrcoef
-            if (Cw) { Cw[(size_t)i * C + j] = r; Cw[(size_t)j * C + i] = r; }
-            if (Dw) {
-                double d;
-                if (method == 0) d = sqrt(2.0 * (1.0 - r));
-                else if (method == 1) d = 1.0 - fabs(r);
-                else if (method == 2) d = 1.0 - r;
-                else d = sqrt(1.0 - r * r);
-                d = fmax(d, 0.0);
-                if (i == j) d = 0.0;
-                const float f = (float)d;
-                Dw[(size_t)i * C + j] = f;
-                Dw[(size_t)j * C + i] = f;
+        for (int e0 = tid; e0 < npairs; e0 += kMmaThreads * kPairsPerThread) {
+            int pi[kPairsPerThread], pj[kPairsPerThread];
+            double r[kPairsPerThread], d[kPairsPerThread];
+            bool ok[kPairsPerThread];
+#pragma unroll
+            for (int q = 0; q < kPairsPerThread; ++q) {
+                const int e = e0 + q * kMmaThreads;
+                const int ec = e < npairs ? e : 0;
+                // ec / half without an integer division (exact: ec + 0.5 is half a unit away from every multiple)
+                const int r0 = __float2int_rz(((float)ec + 0.5f) * inv_half), o = ec - r0 * half;
+                int r1 = r0 + o;
+                if (r1 >= C) r1 -= C;
+                // even C: the antipodal pairs come twice
+                ok[q] = e < npairs && !(C % 2 == 0 && o == C / 2 && r0 >= C / 2);
+                pi[q] = r0 < r1 ? r0 : r1;
+                pj[q] = r0 < r1 ? r1 : r0;
+                const int ti = pi[q] >> 3, tj = pj[q] >> 3;
+                r[q] = cs[(size_t)(ti * nt - ti * (ti - 1) / 2 + tj - ti) * 64 + (pi[q] & 7) * 8 + (pj[q] & 7)];
+            }
+#pragma unroll
+            for (int q = 0; q < kPairsPerThread; ++q) r[q] = r[q] / sd[pi[q]];
+#pragma unroll
+            for (int q = 0; q < kPairsPerThread; ++q) r[q] = r[q] / sd[pj[q]];   // numpy: c /= stddev[:, None]; c /= stddev[None, :]
+#pragma unroll
+            for (int q = 0; q < kPairsPerThread; ++q) {
+                if (r[q] != r[q]) r[q] = 0.0;                  // nan_to_num(nan=0.0): zero-variance channel
+                else r[q] = fmin(fmax(r[q], -1.0), 1.0);       // np.clip inside corrcoef
+                double t;
+                if (method == 0) t = 2.0 * (1.0 - r[q]);
+                else if (method == 1) t = 1.0 - fabs(r[q]);
+                else if (method == 2) t = 1.0 - r[q];
+                else t = 1.0 - r[q] * r[q];
+                d[q] = t;
+            }
+            if (method == 0 || method == 3) {
+#pragma unroll
+                for (int q = 0; q < kPairsPerThread; ++q) d[q] = sqrt(d[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < kPairsPerThread; ++q) {
+                if (!ok[q]) continue;
+                const int i = pi[q], j = pj[q];
+                if (Cw) { Cw[(size_t)i * C + j] = r[q]; Cw[(size_t)j * C + i] = r[q]; }
+                if (Dw) {
+                    double dd = fmax(d[q], 0.0);
+                    if (i == j) dd = 0.0;
+                    const float f = (float)dd;
+                    Dw[(size_t)i * C + j] = f;
+                    Dw[(size_t)j * C + i] = f;
+                }
             }
         }
-        __syncthreads();
+        __syncthreads();   // cs and sd are free for the next window
+        rec += step_rec;
+        w += step_w;
+        if (w >= W) { w -= W; ++rec; }
     }
 }
 
 size_t corrdist_mma_smem_bytes(int C, int win) {
     const int Cp = (C + 7) & ~7;
     const int nt = Cp / 8, ntiles = nt * (nt + 1) / 2;
-    const int rounds = (ntiles + kMmaWarps * kIlp - 1) / (kMmaWarps * kIlp);
-    size_t doubles = (size_t)Cp * mma_ldw(win) + Cp;
-    if (rounds > 1) doubles += (size_t)Cp * Cp;
-    if (rounds == 1 && (size_t)Cp * Cp > (size_t)Cp * mma_ldw(win)) doubles = (size_t)Cp * Cp + Cp;   // tiny windows
-    return doubles * sizeof(double);
+    return ((size_t)Cp * mma_ldw(win) + (size_t)ntiles * 64 + Cp) * sizeof(double) + 2 * sizeof(uint64_t);
 }
 
-// returns a cudaError_t / TDA_E_* like the C-ABI; the caller has validated the arguments
+// returns a cudaError_t / TDA_E_* like the C-ABI; the caller has validated the arguments.  TDA_E_SIZE:
+// a shape this kernel does not take (the caller falls back to corrdist_kernel)
 int launch_corrdist_mma(const double* x, int R, int C, long long T, long long strideR, int win, int step, long long W,
                         int method, float* D, double* corr, long long strideO, cudaStream_t stream) {
+    const int Cp = (C + 7) & ~7;
+    const int nt = Cp / 8, ntiles = nt * (nt + 1) / 2;
+    if (ntiles > kMmaWarps * kIlp || C > 64) return TDA_E_SIZE;                        // one round of tiles
     const size_t smem = corrdist_mma_smem_bytes(C, win);
     if (smem > 227 * 1024) return TDA_E_SIZE;
-    if ((size_t)((C + 7) & ~7) * ((C + 7) & ~7) > (size_t)((C + 7) & ~7) * mma_ldw(win)) return TDA_E_SIZE;   // cs must fit over xs
+    // bulk copies: 16-byte aligned sources and sizes
+    if (((uintptr_t)x & 15) || (T & 1) || (strideR & 1) || (step & 1) || (win & 1)) return TDA_E_SIZE;
     cudaError_t e = cudaFuncSetAttribute(corrdist_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int per_sm = (int)((228 * 1024) / (smem + 1024));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 2) per_sm = 2;
     long long items = (long long)R * W;
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm > 2) per_sm = 2;
     long long grid = (long long)sms * per_sm;
     if (grid > items) grid = items;
     tda::ProfScope prof("corrdist_mma", stream);

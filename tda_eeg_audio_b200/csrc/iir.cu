@@ -11,17 +11,19 @@
 // update order in FP64, without FMA contraction, lands on the reference's numbers.
 //
 // Mapping: one thread owns one (band, sequence) job — the recursion is serial in time, and at the
-// benchmark shape there are 332,760 independent jobs.  A CTA of 128 jobs of ONE band (its
-// coefficients pinned in registers: the recursion's SASS is 36 DMUL/DADD per sample and nothing
-// else) moves time tiles of 16 samples through shared memory so that every HBM access is a
-// coalesced 128-byte row segment (lanes along time on the way in/out, lanes along jobs inside the
-// recursion; odd row stride keeps both conflict-free).  The staging is software-pipelined: while the
-// CTA runs the recursion on tile q, the sixteen values each thread contributes to tile q+1 are in
-// flight from HBM into its registers.  The forward pass materialises the padded intermediate once
-// (workspace); the backward pass walks the same tiles in reverse and writes only the un-padded
-// samples.  Measured against the two earlier generations of this kernel (coefficients from the
-// constant bank; unpipelined staging), outputs bit-equal: 27.9 / 16.8 / 9.9 ms for the five EEG bands
-// of 256 recordings (profiles/r02_staged_ab.jsonl).
+// benchmark shape there are 332,760 independent jobs.  A CTA holds 32 sequences x ALL bands: warp =
+// band (its coefficients pinned in registers: the recursion's SASS is 36 DMUL/DADD per sample and
+// nothing else), lane = sequence, so a recording is read from HBM once for all its bands.  What bounds
+// the kernel is the memory path, not the FP64 pipe (a copy-only build of the previous generation ran
+// in 90 % of the time of the real one; profiles/README.md), so the layout serves HBM:
+//   * the padded intermediate between the two passes is stored TIME-MAJOR per CTA group,
+//     mid[group][k][band*32 + seq]: the forward pass writes each sample of all its jobs as one
+//     contiguous 1,280-byte row straight from registers, the backward pass streams whole 20 KB tiles
+//     back with 16-byte cp.async copies — no 128-byte row segments at 120 KB strides;
+//   * input tiles (forward: 32 channel rows x 16 samples; backward: 16 time rows of the intermediate)
+//     are staged two tiles ahead with cp.async into a ring of three shared-memory tiles PER WARP (no
+//     CTA-wide barrier anywhere in the steady state), filtered in place, and only the backward pass
+//     transposes through shared memory to write the un-padded samples as coalesced row segments of y.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -32,10 +34,10 @@
 namespace tda {
 namespace iir {
 
-constexpr int kJobs = 128;   // threads per CTA = jobs per CTA
-constexpr int kTT = 16;      // samples per time tile (36 KB of staging per CTA)
-constexpr int kRPW = 32 / kTT;  // tile rows one warp moves per step
-constexpr int kLd = kTT + 1; // odd row stride
+constexpr int kSeq = 32;     // sequences per CTA (lanes); warps = bands
+constexpr int kTT = 16;      // samples per time tile
+constexpr int kLdIn = kTT + 1;  // row stride of a forward input tile (odd: lanes = rows read conflict-free)
+constexpr int kRing = 3;     // tiles in flight per CTA
 constexpr int kMaxBands = 8;
 constexpr int kMaxSec = 4;   // sos sections
 constexpr int kMaxTaps = 9;  // ba taps
@@ -52,8 +54,16 @@ struct Coef {
 //   sos: scipy _sosfilt: x_new = b0*x + z0 ; z0 = b1*x - a1*x_new + z1 ; z1 = b2*x - a2*x_new
 //   ba : scipy lfilter (direct form II transposed):
 //        y = Z[0] + b[0]*x ; Z[n] = Z[n+1] + x*b[n+1] - y*a[n+1] ; Z[last] = x*b[last] - y*a[last]
-template <int FORM>
-__device__ __forceinline__ double step_regs(double (&z)[8], const double (&cr)[kMaxSec * 6], int n, double x) {
+// NC > 0: the number of sections / taps is a compile-time constant, so a whole tile of the recursion is
+// straight-line code that the scheduler interleaves across sections and samples (with the run-time
+// count every section is a basic block of its own: measured 43 % of the FP64 pipe at full occupancy,
+// profiles/r02b_iir_forward_ncu.json)
+template <int FORM, int NC>
+__device__ __forceinline__ double step_regs(double (&z)[8], const double (&cr)[kMaxSec * 6], int n_rt, double x) {
+    const int n = NC > 0 ? NC : n_rt;
+#ifdef IIR_COPY_ONLY
+    return x;
+#endif
     if (FORM == 0) {
 #pragma unroll
         for (int s = 0; s < kMaxSec; ++s) {
@@ -91,106 +101,196 @@ __device__ __forceinline__ double ext_value(const double* __restrict__ x, long l
 // jobs are (band, seq): job = band * n_seq + seq; a CTA works on groups of 128 sequences of one band
 //   forward : in = x (n_seq rows, stride x_stride), out = mid (n_jobs rows of Text)
 //   backward: in = mid, out = y (n_jobs rows of T, row stride T)
-template <int FORM, bool BACKWARD>
-__global__ void __launch_bounds__(kJobs, 4) iir_pass_kernel(const double* __restrict__ in, double* __restrict__ out,
-                                                            long long n_seq, int n_bands, long long T,
-                                                            long long x_stride, int edge,
-                                                            const __grid_constant__ Coef cf) {
-    extern __shared__ __align__(16) double iir_smem[];
-    double* tin = iir_smem;
-    double* tout = iir_smem + kJobs * kLd;
-    long long* inbase = reinterpret_cast<long long*>(iir_smem + 2 * kJobs * kLd);   // element offset of a job's input row
-    long long* outbase = inbase + kJobs;                                             // ... of its output row
-    constexpr int kRows = kJobs / ((kJobs / 32) * kRPW);   // rows of a tile one thread moves (16)
-    constexpr int kRStep = (kJobs / 32) * kRPW;            // distance between them (8)
-    const long long Text = T + 2LL * edge;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int r0 = warp * kRPW + lane / kTT;   // first tile row of this thread
-    const int c = lane % kTT;                  // its column (time within the tile)
-    const long long n_tiles = (Text + kTT - 1) / kTT;
-    // job groups: ceil(n_seq / 128) groups per band, each within one band
-    const long long gpb = (n_seq + kJobs - 1) / kJobs;
-    const long long n_groups = gpb * n_bands;
-    for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-        const int band = (int)(grp / gpb);                                   // uniform in the CTA
-        const long long seq0 = (grp - (long long)band * gpb) * kJobs;
-        const long long job = (long long)band * n_seq + seq0 + tid;
-        const bool active = seq0 + tid < n_seq;
-        double cr[kMaxSec * 6];
+__device__ __forceinline__ void cp_async_8(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_16(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int FORM> __device__ __forceinline__ void load_coefficients(const Coef& cf, int band, double (&cr)[kMaxSec * 6]) {
 #pragma unroll
-        for (int k = 0; k < kMaxSec * 6; ++k) {
-            const bool used = FORM == 0 ? (k % 6 != 3) : (k < 2 * kMaxTaps);
-            cr[k] = used ? cf.c[band][k] : 0.0;
-            if (used) asm volatile("" : "+d"(cr[k]));   // a register, not a constant-bank operand
-        }
-        __syncthreads();   // the previous group's last tile has left tin / tout / the offset tables
-        inbase[tid] = active ? (BACKWARD ? job * Text : (seq0 + tid) * x_stride) : 0;
-        outbase[tid] = active ? (BACKWARD ? job * T : job * Text) : 0;
+    for (int k = 0; k < kMaxSec * 6; ++k) {
+        const bool used = FORM == 0 ? (k % 6 != 3) : (k < 2 * kMaxTaps);
+        cr[k] = used ? cf.c[band][k] : 0.0;
+        if (used) asm volatile("" : "+d"(cr[k]));   // a register, not a constant-bank operand
+    }
+}
+
+// Forward pass.  blockDim.x = 32 * n_bands; group g = sequences [32 g, 32 g + 32); warp = band.
+//   in  = x (n_seq rows of T samples, stride x_stride)
+//   out = mid, time-major per group: mid[(g * Text + k) * nth + band * 32 + lane], nth = blockDim.x
+// Every warp is autonomous (its own ring of tiles, __syncwarp only): with CTA-wide barriers the five
+// warps of a CTA, spread unevenly over four schedulers, waited for one another 2.5 cycles per issued
+// instruction (profiles/r02c_iir_forward_ncu.json).  The bands of a group read the same x tile; the
+// copies after the first hit L1 / L2.
+template <int FORM, int NC>
+__global__ void __launch_bounds__(kSeq * kMaxBands, 2) iir_forward_kernel(const double* __restrict__ x, double* __restrict__ mid,
+                                                                          long long n_seq, long long T, long long x_stride,
+                                                                          int edge, const __grid_constant__ Coef cf) {
+    extern __shared__ __align__(16) double iir_smem[];   // per warp: ring of kRing tiles [32 rows][kLdIn]
+    const long long Text = T + 2LL * edge;
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, band = tid >> 5;
+    double* ring = iir_smem + band * (kRing * kSeq * kLdIn);
+    const int r0 = lane >> 4, c = lane & 15;   // staging: rows r0, r0 + 2, ..., column c
+    const long long n_tiles = (Text + kTT - 1) / kTT;
+    const long long n_groups = (n_seq + kSeq - 1) / kSeq;
+    double cr[kMaxSec * 6];
+    load_coefficients<FORM>(cf, band, cr);
+    for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const long long seq0 = grp * kSeq;
+        const bool active = seq0 + lane < n_seq;
+        const int rows_here = (int)(n_seq - seq0 < kSeq ? n_seq - seq0 : kSeq);
+        const double* x_row0 = x + seq0 * x_stride;
+        double* mid_g = mid + grp * Text * nth;
+        __syncwarp();   // the previous group's last tile has been read
         double z[8];
         if (active) {
-            double scale;
-            if (!BACKWARD) scale = ext_value(in + (seq0 + tid) * x_stride, T, edge, 0);
-            else scale = in[job * Text + (Text - 1)];
+            const double scale = ext_value(x_row0 + lane * x_stride, T, edge, 0);
 #pragma unroll
             for (int k = 0; k < 8; ++k) z[k] = __dmul_rn(cf.zi[band][k], scale);
         }
-        __syncthreads();
-        const long long left = n_seq - seq0;
-        const int rows_here = (int)(left < kJobs ? left : kJobs);
-        double nx[kRows];
-        // values of tile `tile` this thread stages: rows r0, r0 + 8, ..., column c
-        auto fetch = [&](long long tile) {
+        // stage tile `tile` (32 rows x 16 samples of x, odd-extended at the ends) into ring slot `slot`
+        auto stage = [&](long long tile, int slot) {
+            double* dst = ring + slot * (kSeq * kLdIn) + r0 * kLdIn + c;
             const long long k = tile * kTT + c;
-            const bool interior = BACKWARD || (tile * kTT >= edge && tile * kTT + kTT <= edge + T);
+            const bool interior = tile * kTT >= edge && tile * kTT + kTT <= edge + T;
+            if (k < Text) {
+                if (interior) {
+                    const double* src = x_row0 + r0 * x_stride + (k - edge);
 #pragma unroll
-            for (int i = 0; i < kRows; ++i) {
-                const int r = r0 + kRStep * i;
-                double v = 0.0;
-                if (r < rows_here && k < Text) {
-                    const double* row = in + inbase[r];
-                    if (BACKWARD) v = row[k];
-                    else if (interior) v = row[k - edge];
-                    else v = ext_value(row, T, edge, k);
-                }
-                nx[i] = v;
-            }
-        };
-        fetch(BACKWARD ? n_tiles - 1 : 0);
-#pragma unroll
-        for (int i = 0; i < kRows; ++i) tin[(r0 + kRStep * i) * kLd + c] = nx[i];
-        __syncthreads();
-        for (long long q = 0; q < n_tiles; ++q) {
-            const long long tile = BACKWARD ? (n_tiles - 1 - q) : q;
-            const long long k0 = tile * kTT;
-            if (q + 1 < n_tiles) fetch(BACKWARD ? tile - 1 : tile + 1);   // in flight during the recursion
-            // ---- serial recursion, one job per thread
-            if (active) {
-                const int nvalid = (int)((Text - k0 < kTT) ? (Text - k0) : kTT);
-                if (!BACKWARD) {
-                    for (int cc = 0; cc < nvalid; ++cc)
-                        tout[tid * kLd + cc] = step_regs<FORM>(z, cr, cf.n, tin[tid * kLd + cc]);
+                    for (int i = 0; i < kSeq / 2; ++i) {
+                        if (r0 + 2 * i < rows_here) cp_async_8(dst, src);
+                        src += 2 * x_stride;
+                        dst += 2 * kLdIn;
+                    }
                 } else {
-                    for (int cc = nvalid - 1; cc >= 0; --cc)
-                        tout[tid * kLd + cc] = step_regs<FORM>(z, cr, cf.n, tin[tid * kLd + cc]);
+#pragma unroll 4
+                    for (int i = 0; i < kSeq / 2; ++i) {
+                        const int r = r0 + 2 * i;
+                        if (r < rows_here) dst[2 * i * kLdIn] = ext_value(x_row0 + r * x_stride, T, edge, k);
+                    }
                 }
             }
-            __syncthreads();   // tout complete, tin consumed
-            // ---- cooperative coalesced store of tile q, then the staged tile q + 1 takes tin
+            cp_async_commit();
+        };
+        // (every call commits one cp.async group, so "all but the newest group" = the tile about to be used)
+        stage(0, 0);
+        if (n_tiles > 1) stage(1, 1); else cp_async_commit();
+        int buf = 0;
+        for (long long q = 0; q < n_tiles; ++q) {
+            const long long k0 = q * kTT;
+            cp_async_wait<1>();
+            __syncwarp();   // tile q is in slot buf; every lane has left the slot tile q + 2 goes to
+            if (q + 2 < n_tiles) stage(q + 2, buf == 0 ? kRing - 1 : buf - 1);
+            else cp_async_commit();
+            if (active) {
+                const double* ti = ring + buf * (kSeq * kLdIn) + lane * kLdIn;
+                double* to = mid_g + k0 * nth + tid;
+                const int nvalid = (int)((Text - k0 < kTT) ? (Text - k0) : kTT);
+                if (nvalid == kTT) {
+                    // a full tile is straight-line code: the sections of consecutive samples overlap
+                    double v[kTT];
+#pragma unroll
+                    for (int cc = 0; cc < kTT; ++cc) v[cc] = ti[cc];
+#pragma unroll
+                    for (int cc = 0; cc < kTT; ++cc) to[(long long)cc * nth] = step_regs<FORM, NC>(z, cr, cf.n, v[cc]);
+                } else {
+                    for (int cc = 0; cc < nvalid; ++cc) to[(long long)cc * nth] = step_regs<FORM, NC>(z, cr, cf.n, ti[cc]);
+                }
+            }
+            buf = buf + 1 == kRing ? 0 : buf + 1;
+        }
+    }
+}
+
+// Backward pass: walks the tiles of mid in reverse, writes the un-padded samples of
+//   y[(band * n_seq + seq) * T + k - edge].   Warps autonomous as in the forward pass: a warp streams
+// its own 32 columns of every time row (256 contiguous bytes), filters them in place and writes its 32
+// job rows through a transposed read of its tile (lanes along time: 128-byte row segments).
+constexpr int kLdB = kSeq + 2;   // row stride of a backward tile: rows stay 16-byte aligned, transposed reads 2-way
+template <int FORM, int NC>
+__global__ void __launch_bounds__(kSeq * kMaxBands, 2) iir_backward_kernel(const double* __restrict__ mid, double* __restrict__ y,
+                                                                           long long n_seq, long long T, int edge,
+                                                                           const __grid_constant__ Coef cf) {
+    extern __shared__ __align__(16) double iir_smem[];   // per warp: ring of kRing tiles [16 time rows][kLdB]
+    const long long Text = T + 2LL * edge;
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, band = tid >> 5;
+    double* ring = iir_smem + band * (kRing * kTT * kLdB);
+    const int r0 = lane >> 4, c = lane & 15;
+    const long long n_tiles = (Text + kTT - 1) / kTT;
+    const long long n_groups = (n_seq + kSeq - 1) / kSeq;
+    double cr[kMaxSec * 6];
+    load_coefficients<FORM>(cf, band, cr);
+    for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const long long seq0 = grp * kSeq;
+        const bool active = seq0 + lane < n_seq;
+        const int rows_here = (int)(n_seq - seq0 < kSeq ? n_seq - seq0 : kSeq);
+        const double* mid_w = mid + grp * Text * nth + band * kSeq;   // this warp's 32 columns
+        double* y_row0 = y + ((long long)band * n_seq + seq0) * T;
+        __syncwarp();   // the previous group's last tile has been stored
+        double z[8];
+        if (active) {
+            const double scale = mid_w[(Text - 1) * nth + lane];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) z[k] = __dmul_rn(cf.zi[band][k], scale);
+        }
+        auto stage = [&](long long tile, int slot) {   // 16 time rows of 32 doubles: lane = (row parity, 16-byte piece)
+            double* dst = ring + slot * (kTT * kLdB) + r0 * kLdB + 2 * c;
+            const double* src = mid_w + (tile * kTT + r0) * nth + 2 * c;
+            const int rows = (int)((Text - tile * kTT < kTT) ? (Text - tile * kTT) : kTT);
+#pragma unroll
+            for (int i = 0; i < kTT / 2; ++i) {
+                if (r0 + 2 * i < rows) cp_async_16(dst, src);
+                src += 2 * (long long)nth;
+                dst += 2 * kLdB;
+            }
+            cp_async_commit();
+        };
+        stage(n_tiles - 1, 0);
+        if (n_tiles > 1) stage(n_tiles - 2, 1); else cp_async_commit();
+        int buf = 0;
+        for (long long q = 0; q < n_tiles; ++q) {
+            const long long tile = n_tiles - 1 - q;
+            const long long k0 = tile * kTT;
+            cp_async_wait<1>();
+            __syncwarp();   // tile q is in slot buf; the store of tile q - 1 has read its slot
+            if (q + 2 < n_tiles) stage(tile - 2, buf == 0 ? kRing - 1 : buf - 1);
+            else cp_async_commit();
+            double* slot = ring + buf * (kTT * kLdB);
+            if (active) {
+                double* ti = slot + lane;   // column of this job; filtered in place
+                const int nvalid = (int)((Text - k0 < kTT) ? (Text - k0) : kTT);
+                if (nvalid == kTT) {
+                    double v[kTT];
+#pragma unroll
+                    for (int cc = 0; cc < kTT; ++cc) v[cc] = ti[cc * kLdB];
+#pragma unroll
+                    for (int cc = kTT - 1; cc >= 0; --cc) ti[cc * kLdB] = step_regs<FORM, NC>(z, cr, cf.n, v[cc]);
+                } else {
+                    for (int cc = nvalid - 1; cc >= 0; --cc) ti[cc * kLdB] = step_regs<FORM, NC>(z, cr, cf.n, ti[cc * kLdB]);
+                }
+            }
+            __syncwarp();   // the tile is filtered
+            // ---- transposed, coalesced store: lanes along time (two job rows of 128 bytes per step)
             {
                 const long long k = k0 + c;
-                const bool keep = BACKWARD ? (k >= edge && k < edge + T) : (k < Text);
-                const long long ko = BACKWARD ? k - edge : k;
+                if (k >= edge && k < edge + T) {
+                    double* dst = y_row0 + r0 * T + (k - edge);
+                    const double* sv = slot + c * kLdB + r0;
 #pragma unroll
-                for (int i = 0; i < kRows; ++i) {
-                    const int r = r0 + kRStep * i;
-                    if (keep && r < rows_here) out[outbase[r] + ko] = tout[r * kLd + c];
+                    for (int i = 0; i < kSeq / 2; ++i) {
+                        if (r0 + 2 * i < rows_here) *dst = *sv;
+                        dst += 2 * T;
+                        sv += 2;
+                    }
                 }
             }
-            if (q + 1 < n_tiles) {
-#pragma unroll
-                for (int i = 0; i < kRows; ++i) tin[(r0 + kRStep * i) * kLd + c] = nx[i];
-            }
-            __syncthreads();   // tin holds tile q + 1, tout is free
+            buf = buf + 1 == kRing ? 0 : buf + 1;
         }
     }
 }
@@ -200,7 +300,9 @@ __global__ void __launch_bounds__(kJobs, 4) iir_pass_kernel(const double* __rest
 
 extern "C" size_t tda_filtfilt_workspace_bytes(long long n_seq, int n_bands, long long T, int padlen) {
     if (n_seq < 0 || n_bands < 1 || T < 1 || padlen < 0) return 0;
-    return (size_t)n_seq * n_bands * (size_t)(T + 2LL * padlen) * sizeof(double);
+    // the padded intermediate, time-major per group of 32 sequences (the last group is padded to 32)
+    const long long groups = (n_seq + tda::iir::kSeq - 1) / tda::iir::kSeq;
+    return (size_t)groups * tda::iir::kSeq * n_bands * (size_t)(T + 2LL * padlen) * sizeof(double);
 }
 
 extern "C" int tda_filtfilt_f64(const double* x, long long n_seq, long long T, long long x_stride, int form,
@@ -238,32 +340,41 @@ extern "C" int tda_filtfilt_f64(const double* x, long long n_seq, long long T, l
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long groups = ((n_seq + kJobs - 1) / kJobs) * n_bands;
-    const long long maxb = (long long)sms * 4;  // 128 registers, 36 KB of staging per CTA -> 4 CTAs per SM
+    const long long groups = (n_seq + kSeq - 1) / kSeq;
+    const int nth = kSeq * n_bands;
+    const int smem_f = n_bands * kRing * kSeq * kLdIn * (int)sizeof(double);   // a ring per warp
+    const int smem_b = n_bands * kRing * kTT * kLdB * (int)sizeof(double);
+    // resident CTAs per SM: registers (<= 128 per thread) and the backward pass's staging
+    int per_sm = 65536 / (nth * 128);
+    const int by_smem = (227 * 1024) / ((smem_f > smem_b ? smem_f : smem_b) + 1024);
+    if (per_sm > by_smem) per_sm = by_smem;
+    if (per_sm < 1) per_sm = 1;
+    const long long maxb = (long long)sms * per_sm;
     const int grid = (int)(groups < maxb ? groups : maxb);
     cudaStream_t st = (cudaStream_t)stream;
     double* mid = (double*)ws;
-    const int smem = 2 * kJobs * kLd * (int)sizeof(double) + 2 * kJobs * (int)sizeof(long long);
-    if (form == 0) {
-        cudaFuncSetAttribute(iir_pass_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(iir_pass_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    } else {
-        cudaFuncSetAttribute(iir_pass_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(iir_pass_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    }
-    {
-        tda::ProfScope prof(form == 0 ? "iir_sos_forward" : "iir_ba_forward", st);
-        if (form == 0) iir_pass_kernel<0, false><<<grid, kJobs, smem, st>>>(x, mid, n_seq, n_bands, T, x_stride, padlen, cf);
-        else iir_pass_kernel<1, false><<<grid, kJobs, smem, st>>>(x, mid, n_seq, n_bands, T, x_stride, padlen, cf);
-        tda::count_launch();
-    }
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return (int)e;
-    {
-        tda::ProfScope prof(form == 0 ? "iir_sos_backward" : "iir_ba_backward", st);
-        if (form == 0) iir_pass_kernel<0, true><<<grid, kJobs, smem, st>>>(mid, y, n_seq, n_bands, T, 0, padlen, cf);
-        else iir_pass_kernel<1, true><<<grid, kJobs, smem, st>>>(mid, y, n_seq, n_bands, T, 0, padlen, cf);
-        tda::count_launch();
-    }
-    return (int)cudaGetLastError();
+    // sections / taps known at compile time for the filters of the pipeline (order-4 band-pass: 4 sections
+    // or 9 taps; order-4 low-pass: 5 taps); any other count runs the same kernels with a run-time count
+    auto launch = [&](auto fwd, auto bwd) -> int {
+        cudaFuncSetAttribute(fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f);
+        cudaFuncSetAttribute(bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b);
+        {
+            tda::ProfScope prof(form == 0 ? "iir_sos_forward" : "iir_ba_forward", st);
+            fwd<<<grid, nth, smem_f, st>>>(x, mid, n_seq, T, x_stride, padlen, cf);
+            tda::count_launch();
+        }
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+        {
+            tda::ProfScope prof(form == 0 ? "iir_sos_backward" : "iir_ba_backward", st);
+            bwd<<<grid, nth, smem_b, st>>>(mid, y, n_seq, T, padlen, cf);
+            tda::count_launch();
+        }
+        return (int)cudaGetLastError();
+    };
+    if (form == 0 && n == 4) return launch(iir_forward_kernel<0, 4>, iir_backward_kernel<0, 4>);
+    if (form == 0) return launch(iir_forward_kernel<0, 0>, iir_backward_kernel<0, 0>);
+    if (n == 9) return launch(iir_forward_kernel<1, 9>, iir_backward_kernel<1, 9>);
+    if (n == 5) return launch(iir_forward_kernel<1, 5>, iir_backward_kernel<1, 5>);
+    return launch(iir_forward_kernel<1, 0>, iir_backward_kernel<1, 0>);
 }

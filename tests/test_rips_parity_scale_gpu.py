@@ -73,13 +73,18 @@ def test_tie_heavy_20k_windows_bit_exact(cuda):
     D = dsp.eeg_distances_from_raw(x, overlap=0.0).view(-1, 47, 47)
     Dq = torch.round(D * 64) / 64
     tq = _gpu_vs_oracle(Dq, "quantised 1/64")
-    x[:, 9] = x[:, 8]
-    x[:, 20] = -x[:, 3]
-    x[:, 5] = 2.5
-    Dd = dsp.eeg_distances_from_raw(x, overlap=0.0).view(-1, 47, 47)
+    # degenerate channels in the BAND-PASSED signal (a constant raw channel is rounding noise after the filter)
+    import numpy as np
+    sos = np.stack([dsp.design_bandpass_filter(lo, hi, 250) for lo, hi in dsp.FREQ_BANDS.values()])
+    R, C, T = x.shape
+    filt = dsp.sosfiltfilt_batched(x.view(R * C, T), sos).view(5, R, C, T)
+    filt[:, :, 9] = filt[:, :, 8]
+    filt[:, :, 20] = -filt[:, :, 3]
+    filt[:, :, 5] = 2.5
+    Dd = torch.stack([dsp.corrdist_windows(filt[b], 250, 250) for b in range(5)]).view(-1, 47, 47)
     # (numpy's own c / sd_i / sd_j of a duplicated channel is 1 or 1 - 2^-53: d = 0 or ~1.5e-8)
     assert float(Dd[:, 8, 9].max()) < 1e-7 and bool((Dd[:, 8, 9] == 0).any())
-    assert bool((Dd[:, 5, 6] == Dd[:, 5, 30]).all())
+    assert bool((Dd[:, 5, 6] == Dd[:, 5, 30]).all()) and abs(float(Dd[0, 5, 6]) - 2 ** 0.5) < 1e-6
     assert float(Dd[:, 3, 20].min()) > 1.9999
     td = _gpu_vs_oracle(Dd, "duplicate / negated / constant channel")
     print("tier counts, quantised:", tq, " degenerate channels:", td)
