@@ -11,10 +11,13 @@
 // Here (oracle/pcoh_large_model.cpp is the executable statement of the algorithm, validated on
 // CPU) the work is split into grid-wide data-parallel phases over ALL clouds of a chunk and a
 // short serial sweep per cloud:
-//   K1 keys      one 64-bit key per edge: cloud | order-preserving image of the f32 length | ~index
-//                (so ONE device-wide radix sort (CUB) orders every cloud by (length asc, index desc),
-//                Ripser's tie-break)
-//   K2 scatter   sorted position r -> P[r] = (i, j, tie flag), rank matrix T[i][j] = r
+//   K1 rank      one CTA per cloud: the order-preserving integer image of every f32 edge length, laid out in
+//                descending edge index, then a stable LSD radix sort of (key, (i, j)) -- 8-bit digits, a
+//                segment of the array and a row of digit counters per warp, __match_any_sync ranks inside a
+//                chunk of 32, passes over bytes equal in all keys skipped -- whose stability yields Ripser's
+//                tie-break (equal length => larger index first); sorted position r -> P[r] = (i, j, tie
+//                flag), rank matrix T[i][j] = r (16-bit ranks up to 256 points: half the bytes of the table
+//                every later phase reads by rows)
 //   K3 kruskal   one CTA per cloud: MST flags + the H0 pairs (elder rule for the vertex)
 //   K4 classify  one thread per edge, cooperative over the whole grid: the first cofacet of every
 //                non-MST edge (largest apex v with T[i][v], T[j][v] inside the edge's tie run or
@@ -38,8 +41,6 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
-
-#include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
 #include "tda_b200.h"
@@ -88,10 +89,10 @@ struct Params {
     int c0, C;
     int ldT, ib;
     long long Emax;
-    uint64_t* keysA;
-    uint64_t* keysB;
+    uint32_t* sortbuf; // [C][4][Emax]: keys / payloads, ping and pong
+    uint32_t* skey;   // [C][Emax] sorted keys (classification of tie runs)
     uint32_t* P;      // [C][Emax]
-    uint32_t* T;      // [C][N][ldT]
+    void* T;          // [C][N][ldT] rank matrix, uint16_t (N <= 256) or uint32_t; all ones = edge absent
     uint16_t* Q;      // [C][N][ldT]
     uint16_t* defv;   // [C][Emax]
     int* m;           // [C] number of edges <= thresh
@@ -114,59 +115,190 @@ __device__ __forceinline__ int cloud_n(const Params& p, int b) {
     return n < 0 ? 0 : (n > p.N ? p.N : n);
 }
 
-// ------------------------------------------------------------------------------------ K1 keys
-// thread per matrix element (row j, column i > j), coalesced along i; padding entries filled too
-__global__ void keys_kernel(Params p) {
-    const int c = blockIdx.y;
-    const int b = p.c0 + c;
-    const int n = cloud_n(p, b);
-    const long long E = c2(n);
-    const uint64_t cbits = (uint64_t)c << (32 + p.ib);
-    const uint64_t imask = (1ull << p.ib) - 1ull;
-    uint64_t* out = p.keysA + (size_t)c * p.Emax;
-    const float* Db = p.D + (size_t)b * p.strideB;
-    int nan_seen = 0;
-    const long long total = (long long)n * n;
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
-        const int j = (int)(q / n), i = (int)(q - (long long)j * n);
-        if (i <= j) continue;
-        const float d = Db[(size_t)j * p.ld + i] + 0.0f;
-        nan_seen |= (d != d);
-        const uint32_t k32 = (d <= p.thresh) ? float_key(d) : kInf;
-        const uint64_t idx = (uint64_t)(c2(i) + j);
-        const long long pos = (long long)j * n - (long long)j * (j + 1) / 2 + (i - j - 1);
-        out[pos] = cbits | ((uint64_t)k32 << p.ib) | (~idx & imask);
-    }
-    for (long long q = E + (long long)blockIdx.x * blockDim.x + threadIdx.x; q < p.Emax; q += (long long)gridDim.x * blockDim.x)
-        out[q] = cbits | ((uint64_t)kInf << p.ib) | imask;
-    if (nan_seen) atomicOr(p.nanflag + c, 1);
-}
+// ------------------------------------------------------------------------------------ K1 rank
+template <typename TT> struct RankOf;
+template <> struct RankOf<uint16_t> { static constexpr uint32_t kAbsent = 0xFFFFu; };
+template <> struct RankOf<uint32_t> { static constexpr uint32_t kAbsent = 0xFFFFFFFFu; };
 
-// ------------------------------------------------------------------------------------ K2 scatter
-__global__ void scatter_kernel(Params p) {
-    const int c = blockIdx.y;
-    const uint64_t* in = p.keysB + (size_t)c * p.Emax;
-    const uint64_t imask = (1ull << p.ib) - 1ull;
-    uint32_t* Pc = p.P + (size_t)c * p.Emax;
-    uint32_t* Tc = p.T + (size_t)c * p.N * p.ldT;
-    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < p.Emax; r += (long long)gridDim.x * blockDim.x) {
-        const uint64_t key = in[r];
-        const uint32_t k32 = (uint32_t)(key >> p.ib);
-        if (k32 == kInf) {
-            if (r == 0) p.m[c] = 0;
-            continue;
+// One CTA of 1,024 threads per cloud, one CTA per SM (the ping-pong arrays of the resident clouds stay
+// in L2).  A pass works through the array in tiles of 8,192 elements: every warp ranks its 256 elements
+// of the tile (a row of 16-bit digit counters per warp, __match_any_sync inside a chunk of 32), the tile
+// is staged in shared memory ordered by digit, and written out as runs (a digit's elements of one tile
+// are contiguous in the destination): full sectors instead of scattered 4-byte writes.
+constexpr int kRankThreads = 1024;
+constexpr int kRankWarps = kRankThreads / 32;
+constexpr int kRankPerThread = 8;
+constexpr int kRankTile = kRankThreads * kRankPerThread;
+constexpr size_t kRankSmem = (size_t)kRankTile * 8 + (size_t)kRankWarps * 256 * 2 + 4 * 256 * 4 + 64 * 4;
+
+template <typename TT>
+__global__ void __launch_bounds__(kRankThreads, 1) rank_kernel(Params p) {
+    constexpr int NTH = kRankThreads, NW = kRankWarps;
+    extern __shared__ __align__(16) unsigned char rk_raw[];
+    uint2* stage = reinterpret_cast<uint2*>(rk_raw);                                   // [kRankTile] (key, payload)
+    uint16_t* wcnt = reinterpret_cast<uint16_t*>(rk_raw + (size_t)kRankTile * 8);       // [NW][256]
+    uint32_t* gbase = reinterpret_cast<uint32_t*>(wcnt + NW * 256);                     // [256] next free slot per digit
+    uint32_t* gofs = gbase + 256;                                                       // [256] global - local position
+    uint32_t* hist = gofs + 256;                                                        // [256]
+    uint32_t* spare = hist + 256;                                                       // [256]
+    uint32_t* red = spare + 256;                                                        // [64]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int c = blockIdx.x; c < p.C; c += gridDim.x) {
+        const int b = p.c0 + c;
+        const int n = cloud_n(p, b);
+        const int E = (int)c2(n);
+        uint32_t* kA = p.sortbuf + (size_t)c * 4 * p.Emax;
+        uint32_t* pA = kA + p.Emax;
+        uint32_t* kB = pA + p.Emax;
+        uint32_t* pB = kB + p.Emax;
+        TT* Tc = reinterpret_cast<TT*>(p.T) + (size_t)c * p.N * p.ldT;
+        uint16_t* Qc = p.Q + (size_t)c * p.N * p.ldT;
+        const float* Db = p.D + (size_t)b * p.strideB;
+        // ---- tables of this cloud: T = absent, Q = none  (vectorised: ldT is a multiple of 32 entries)
+        {
+            uint4* t4 = reinterpret_cast<uint4*>(Tc);
+            const size_t nt4 = (size_t)n * p.ldT * sizeof(TT) / 16;
+            for (size_t q = tid; q < nt4; q += NTH) t4[q] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            uint4* q4 = reinterpret_cast<uint4*>(Qc);
+            const size_t nq4 = (size_t)n * p.ldT * 2 / 16;
+            for (size_t q = tid; q < nq4; q += NTH) q4[q] = make_uint4(0u, 0u, 0u, 0u);
         }
-        uint32_t nk = kInf;
-        if (r + 1 < p.Emax) nk = (uint32_t)(in[r + 1] >> p.ib);
-        if (nk == kInf) p.m[c] = (int)(r + 1);
-        const long long idx = (long long)(~key & imask);
-        long long i = (long long)((1.0 + sqrt(1.0 + 8.0 * (double)idx)) * 0.5);
-        while (c2(i) > idx) --i;
-        while (c2(i + 1) <= idx) ++i;
-        const int j = (int)(idx - c2(i));
-        Pc[r] = (uint32_t)j | ((uint32_t)i << 11) | (nk == k32 ? kTieNext : 0u);
-        Tc[(size_t)i * p.ldT + j] = (uint32_t)r;
-        Tc[(size_t)j * p.ldT + i] = (uint32_t)r;
+        // ---- keys in descending edge index (a warp per matrix row, lanes along the row: coalesced reads)
+        int valid = 0, nan_seen = 0;
+        uint32_t k_or = 0, k_and = 0xFFFFFFFFu;
+        for (int j = warp; j < n - 1; j += NW) {
+            const float* row = Db + (size_t)j * p.ld;
+            for (int i = j + 1 + lane; i < n; i += 32) {
+                const float d = row[i] + 0.0f;
+                nan_seen |= (d != d);
+                const bool ok = d <= p.thresh;
+                const uint32_t key = ok ? float_key(d) : kInf;
+                const int pos = E - 1 - ((int)c2(i) + j);
+                kA[pos] = key;
+                pA[pos] = (uint32_t)j | ((uint32_t)i << 11);
+                if (ok) { ++valid; k_or |= key; k_and &= key; }
+            }
+        }
+        valid = __reduce_add_sync(kFull, valid);
+        nan_seen = __reduce_or_sync(kFull, nan_seen);
+        k_or = __reduce_or_sync(kFull, k_or);
+        k_and = __reduce_and_sync(kFull, k_and);
+        __syncthreads();   // red[] of the previous cloud has been read
+        if (lane == 0) { red[warp] = (uint32_t)valid; spare[warp] = k_or; spare[NW + warp] = k_and; spare[2 * NW + warp] = (uint32_t)nan_seen; }
+        __syncthreads();   // ... and kA / pA are complete
+        int m = 0;
+        uint32_t vor = 0, vand = 0xFFFFFFFFu, any_nan = 0;
+        for (int w = 0; w < NW; ++w) { m += (int)red[w]; vor |= spare[w]; vand &= spare[NW + w]; any_nan |= spare[2 * NW + w]; }
+        // with absent edges (d > thresh, NaN) in between every pass runs: they have to travel to the end
+        const uint32_t varying = (m < E) ? 0xFFFFFFFFu : (vor ^ vand);
+        uint32_t* srcK = kA; uint32_t* srcP = pA; uint32_t* dstK = kB; uint32_t* dstP = pB;
+        for (int pass = 0; pass < 4; ++pass) {
+            const int sh = 8 * pass;
+            if (!((varying >> sh) & 255u)) continue;
+            // ---- digit histogram of the whole array -> first free slot of every digit
+            __syncthreads();
+            if (tid < 256) hist[tid] = 0;
+            __syncthreads();
+            for (int k = tid; k < E; k += NTH) atomicAdd(&hist[(srcK[k] >> sh) & 255u], 1u);
+            __syncthreads();
+            if (tid < 256) {
+                const uint32_t own = hist[tid];
+                uint32_t incl = own;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(kFull, incl, o);
+                    if (lane >= o) incl += y;
+                }
+                if (lane == 31) red[32 + warp] = incl;
+                asm volatile("bar.sync 1, 256;");       // the eight scanning warps only
+                uint32_t base = 0;
+                for (int w = 0; w < warp; ++w) base += red[32 + w];
+                gbase[tid] = base + incl - own;
+            }
+            __syncthreads();
+            for (int t0 = 0; t0 < E; t0 += kRankTile) {
+                const int nT = E - t0 < kRankTile ? E - t0 : kRankTile;
+                // ---- this warp's 256 elements of the tile, their digits counted into its counter row
+                uint32_t* wc32 = reinterpret_cast<uint32_t*>(wcnt);
+                for (int q = tid; q < NW * 128; q += NTH) wc32[q] = 0;
+                __syncthreads();
+                uint32_t kr[kRankPerThread], pr[kRankPerThread];
+                uint32_t* row32 = wc32 + warp * 128;
+#pragma unroll
+                for (int i = 0; i < kRankPerThread; ++i) {
+                    const int k = warp * (32 * kRankPerThread) + 32 * i + lane;
+                    const bool act = k < nT;
+                    kr[i] = act ? srcK[t0 + k] : 0u;
+                    pr[i] = act ? srcP[t0 + k] : 0u;
+                    if (act) {
+                        const uint32_t dg = (kr[i] >> sh) & 255u;
+                        atomicAdd(row32 + (dg >> 1), 1u << (16 * (dg & 1u)));
+                    }
+                }
+                __syncthreads();
+                // ---- local slot of (digit, warp): exclusive scan in digit-major order
+                if (tid < 256) {
+                    uint32_t run = 0;
+                    for (int w = 0; w < NW; ++w) { const uint32_t t = wcnt[w * 256 + tid]; wcnt[w * 256 + tid] = (uint16_t)run; run += t; }
+                    uint32_t incl = run;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t y = __shfl_up_sync(kFull, incl, o);
+                        if (lane >= o) incl += y;
+                    }
+                    if (lane == 31) red[32 + warp] = incl;
+                    asm volatile("bar.sync 1, 256;");
+                    uint32_t tstart = 0;
+                    for (int w = 0; w < warp; ++w) tstart += red[32 + w];
+                    tstart += incl - run;
+                    for (int w = 0; w < NW; ++w) wcnt[w * 256 + tid] += (uint16_t)tstart;
+                    gofs[tid] = gbase[tid] - tstart;
+                    gbase[tid] += run;
+                    asm volatile("bar.sync 1, 256;");   // red[32..40) is read before the next tile rewrites it
+                }
+                __syncthreads();
+                // ---- stage the tile in digit order (stable: chunks in order, lanes ranked inside a chunk)
+                uint16_t* rowc = wcnt + warp * 256;
+#pragma unroll
+                for (int i = 0; i < kRankPerThread; ++i) {
+                    const int k = warp * (32 * kRankPerThread) + 32 * i + lane;
+                    const bool act = k < nT;
+                    const uint32_t dg = act ? ((kr[i] >> sh) & 255u) : (256u + lane);   // idle lanes: no peers
+                    const uint32_t peers = __match_any_sync(kFull, dg);
+                    if (act) stage[rowc[dg] + __popc(peers & lt)] = make_uint2(kr[i], pr[i]);
+                    __syncwarp();
+                    if (act && (peers & lt) == 0) rowc[dg] += (uint16_t)__popc(peers);
+                    __syncwarp();
+                }
+                __syncthreads();
+                // ---- write the tile out: a digit's elements are a contiguous run in the destination
+                for (int lp = tid; lp < nT; lp += NTH) {
+                    const uint2 e = stage[lp];
+                    const uint32_t g = gofs[(e.x >> sh) & 255u] + lp;
+                    dstK[g] = e.x;
+                    dstP[g] = e.y;
+                }
+                __syncthreads();
+            }
+            uint32_t* t;
+            t = srcK; srcK = dstK; dstK = t;
+            t = srcP; srcP = dstP; dstP = t;
+        }
+        __syncthreads();
+        // ---- sorted position -> P, T, sorted keys
+        uint32_t* Pc = p.P + (size_t)c * p.Emax;
+        uint32_t* sk = p.skey + (size_t)c * p.Emax;
+        for (int r = tid; r < m; r += NTH) {
+            const uint32_t key = srcK[r], pay = srcP[r];
+            const bool tie = r + 1 < m && srcK[r + 1] == key;
+            const int i = (int)(pay >> 11), j = (int)(pay & 2047u);
+            Pc[r] = pay | (tie ? kTieNext : 0u);
+            sk[r] = key;
+            Tc[(size_t)i * p.ldT + j] = (TT)r;
+            Tc[(size_t)j * p.ldT + i] = (TT)r;
+        }
+        if (tid == 0) { p.m[c] = n >= 2 ? m : 0; p.nanflag[c] = any_nan ? 1 : 0; }
     }
 }
 
@@ -275,7 +407,10 @@ template <int NTH> __global__ void __launch_bounds__(NTH) kruskal_kernel(Params 
 // Lanes of a warp hold consecutive ranks, i.e. edges of nearly equal length whose neighbourhoods
 // are equally dense, so their scans have similar lengths (~2 sqrt(N) on average: most edges are
 // late and find an apex within the first few candidates).
+template <typename TT>
 __global__ void __launch_bounds__(256) classify_kernel(Params p) {
+    constexpr int VPL = 16 / (int)sizeof(TT);   // ranks per 16-byte load
+    constexpr uint32_t kAbsent = RankOf<TT>::kAbsent;
     const long long total = p.Emax * p.C;
     for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(w / p.Emax);
@@ -285,31 +420,33 @@ __global__ void __launch_bounds__(256) classify_kernel(Params p) {
         const uint32_t q = Pc[r];
         if (q & kMst) continue;
         const int n = cloud_n(p, p.c0 + c);
-        const uint32_t* Tc = p.T + (size_t)c * p.N * p.ldT;
-        const uint64_t* keys = p.keysB + (size_t)c * p.Emax;
+        const TT* Tc = reinterpret_cast<const TT*>(p.T) + (size_t)c * p.N * p.ldT;
+        const uint32_t* keys = p.skey + (size_t)c * p.Emax;
         const int i = p_i(q), j = p_j(q);
         const bool tied = (q & kTieNext) || (r > 0 && (Pc[r - 1] & kTieNext));
-        const uint32_t k32r = tied ? (uint32_t)(keys[r] >> p.ib) : 0u;
+        const uint32_t k32r = tied ? keys[r] : 0u;
         const uint4* Ti = reinterpret_cast<const uint4*>(Tc + (size_t)i * p.ldT);
         const uint4* Tj = reinterpret_cast<const uint4*>(Tc + (size_t)j * p.ldT);
         int dv = -1;
         bool found = false;
-        for (int v4 = (n - 1) >> 2; v4 >= 0 && !found; --v4) {
-            const uint4 a4 = __ldg(Ti + v4), b4 = __ldg(Tj + v4);
-            const uint32_t ta[4] = {a4.x, a4.y, a4.z, a4.w}, tb[4] = {b4.x, b4.y, b4.z, b4.w};
+        for (int vb = (n - 1) / VPL; vb >= 0 && !found; --vb) {
+            const uint4 a4 = __ldg(Ti + vb), b4 = __ldg(Tj + vb);
+            const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w}, bw[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-            for (int k = 3; k >= 0; --k) {
-                if (found || 4 * v4 + k >= n) continue;
-                bool ina = ta[k] < (uint32_t)r, inb = tb[k] < (uint32_t)r;
+            for (int k = VPL - 1; k >= 0; --k) {
+                if (found || VPL * vb + k >= n) continue;
+                const uint32_t ta = sizeof(TT) == 4 ? aw[k] : ((aw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu);
+                const uint32_t tb = sizeof(TT) == 4 ? bw[k] : ((bw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu);
+                bool ina = ta < (uint32_t)r, inb = tb < (uint32_t)r;
                 const bool strict = ina && inb;
                 if (tied) {
                     // an edge of the same tie run that comes later in the order is present too
-                    if (!ina && ta[k] != kInf && ta[k] > (uint32_t)r) ina = (uint32_t)(keys[ta[k]] >> p.ib) == k32r;
-                    if (!inb && tb[k] != kInf && tb[k] > (uint32_t)r) inb = (uint32_t)(keys[tb[k]] >> p.ib) == k32r;
+                    if (!ina && ta != kAbsent && ta > (uint32_t)r) ina = keys[ta] == k32r;
+                    if (!inb && tb != kAbsent && tb > (uint32_t)r) inb = keys[tb] == k32r;
                 }
                 if (ina && inb) {
                     found = true;
-                    dv = strict ? 4 * v4 + k : -1;   // the first cofacet must have the edge as youngest edge
+                    dv = strict ? VPL * vb + k : -1;   // the first cofacet must have the edge as youngest edge
                 }
             }
         }
@@ -319,7 +456,8 @@ __global__ void __launch_bounds__(256) classify_kernel(Params p) {
 }
 
 // ------------------------------------------------------------------------------------ K5 sweep
-template <int NTH, int APT, int W, bool SG> struct Sweep {
+template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
+    static constexpr uint32_t kAbsent = RankOf<TT>::kAbsent;
     // shared state
     uint32_t* S;      // [n][W]  (shared or global)
     uint32_t* hot;    // [kMaxN / 32]
@@ -338,7 +476,7 @@ template <int NTH, int APT, int W, bool SG> struct Sweep {
     uint32_t* rec;
     // per-cloud
     const uint32_t* P;
-    const uint32_t* T;
+    const TT* T;
     uint16_t* Q;
     const uint16_t* defv;
     const float* Db;
@@ -475,12 +613,12 @@ template <int NTH, int APT, int W, bool SG> struct Sweep {
                 const int x = p_i(pq), y = p_j(pq);
                 uint32_t pe[W];
                 load_pe(x, y, pe);
-                const uint32_t* Tx = T + (size_t)x * ldT;
-                const uint32_t* Ty = T + (size_t)y * ldT;
+                const TT* Tx = T + (size_t)x * ldT;
+                const TT* Ty = T + (size_t)y * ldT;
 #pragma unroll
                 for (int h = APT - 1; h >= 0; --h) {
                     const int z = tid + h * NTH;
-                    if (z < n && __ldg(Tx + z) < (uint32_t)pr && __ldg(Ty + z) < (uint32_t)pr) {
+                    if (z < n && (uint32_t)__ldg(Tx + z) < (uint32_t)pr && (uint32_t)__ldg(Ty + z) < (uint32_t)pr) {
                         uint32_t c[W];
                         if (cob(pe, x, y, z, c)) {
                             const uint32_t t = tri_index(x, y, z) + 1u;
@@ -581,8 +719,8 @@ template <int NTH, int APT, int W, bool SG> struct Sweep {
     // anything dies (almost never), only then the general death loop runs
     __device__ void fast_single(int pr, uint32_t pe, int dv) {
         const int x = p_i(pe), y = p_j(pe);
-        const uint32_t* Tx = T + (size_t)x * ldT;
-        const uint32_t* Ty = T + (size_t)y * ldT;
+        const TT* Tx = T + (size_t)x * ldT;
+        const TT* Ty = T + (size_t)y * ldT;
         const uint16_t* Qx = Q + (size_t)x * ldT;
         const uint16_t* Qy = Q + (size_t)y * ldT;
         uint32_t ta[APT], tb[APT];
@@ -590,7 +728,7 @@ template <int NTH, int APT, int W, bool SG> struct Sweep {
 #pragma unroll
         for (int h = 0; h < APT; ++h) {
             const int z = tid + h * NTH;
-            ta[h] = kInf; tb[h] = kInf; qa[h] = 0; qb[h] = 0;
+            ta[h] = kAbsent; tb[h] = kAbsent; qa[h] = 0; qb[h] = 0;
             if (z < n) { ta[h] = __ldg(Tx + z); tb[h] = __ldg(Ty + z); qa[h] = Qx[z]; qb[h] = Qy[z]; }
         }
         if (warp == 0) {
@@ -630,7 +768,7 @@ template <int NTH, int APT, int W, bool SG> struct Sweep {
         ldT = p.ldT;
         ld = p.ld;
         P = p.P + (size_t)c * p.Emax;
-        T = p.T + (size_t)c * p.N * p.ldT;
+        T = reinterpret_cast<const TT*>(p.T) + (size_t)c * p.N * p.ldT;
         Q = p.Q + (size_t)c * p.N * p.ldT;
         defv = p.defv + (size_t)c * p.Emax;
         Db = p.D + (size_t)b * p.strideB;
@@ -763,10 +901,10 @@ template <int NTH, int APT, int W, bool SG> struct Sweep {
     }
 };
 
-template <int NTH, int APT, int W, bool SG>
+template <int NTH, int APT, int W, bool SG, typename TT>
 __global__ void __launch_bounds__(NTH) sweep_kernel(Params p, int rezero_q) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Sweep<NTH, APT, W, SG> s;
+    Sweep<NTH, APT, W, SG, TT> s;
     uint32_t* base = (uint32_t*)smem_raw;
     s.hot = base;            base += kMaxN / 32;
     s.live = base;           base += W;
@@ -805,8 +943,8 @@ template <int W> static size_t sweep_smem(int N, bool sg) {
 struct Plan {
     int N, ldT, ib, C, grid1, grid2, nth, apt, capP, capR;
     long long Emax;
-    size_t cub_bytes;
-    size_t keysA, keysB, P, T, Q, defv, m, nanflag, counters, list, list0, cub, phic1, phic2, pcr, act, rec, sglob, total;
+    int tbytes;   // bytes per rank of T: 2 up to 256 points, else 4
+    size_t sortbuf, skey, P, T, Q, defv, m, nanflag, counters, list, list0, phic1, phic2, pcr, act, rec, sglob, total;
 };
 static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 static int bits_for(long long v) { int b = 1; while ((1ll << b) < v) ++b; return b; }
@@ -831,12 +969,12 @@ static bool make_plan(int B, int N, size_t ws_bytes, Plan& pl) {
     pl.ib = bits_for(pl.Emax);
     pl.nth = N <= 128 ? 32 : (N <= 256 ? 64 : 256);
     pl.apt = N <= 256 ? 4 : (N <= 512 ? 2 : (N <= 1024 ? 4 : 8));
+    pl.tbytes = N <= 256 ? 2 : 4;
     long long cp = 64ll * N;
     pl.capP = (int)(cp < kCapPMax ? cp : kCapPMax);
     pl.capR = (int)(pl.Emax < kCapRMax ? (pl.Emax < 64 ? 64 : pl.Emax) : kCapRMax);
-    const int cmax_bits = 32 - pl.ib;
-    long long cmax = 1ll << (cmax_bits > 15 ? 15 : cmax_bits);   // also the gridDim.y limit
-    const long long cap_items = (1ll << 31) - 1;
+    long long cmax = 1ll << 15;
+    const long long cap_items = (1ll << 31) - 1;   // classify_kernel indexes (cloud, edge) pairs of a chunk
     if (cmax * pl.Emax > cap_items) cmax = cap_items / pl.Emax;
     if (cmax < 1) cmax = 1;
     const int per_sm = tier1_ctas_per_sm(N, pl.nth);
@@ -850,16 +988,12 @@ static bool make_plan(int B, int N, size_t ws_bytes, Plan& pl) {
         pl.nanflag = o; o += al((size_t)C * 4);
         pl.list = o; o += al((size_t)C * 4);
         pl.list0 = o; o += al((size_t)C * 4);
-        pl.keysA = o; o += al((size_t)C * pl.Emax * 8);
-        pl.keysB = o; o += al((size_t)C * pl.Emax * 8);
+        pl.sortbuf = o; o += al((size_t)C * pl.Emax * 16);
+        pl.skey = o; o += al((size_t)C * pl.Emax * 4);
         pl.P = o; o += al((size_t)C * pl.Emax * 4);
         pl.defv = o; o += al((size_t)C * pl.Emax * 2);
-        pl.T = o; o += al((size_t)C * N * pl.ldT * 4);
+        pl.T = o; o += al((size_t)C * N * pl.ldT * pl.tbytes);
         pl.Q = o; o += al((size_t)C * N * pl.ldT * 2);
-        pl.cub_bytes = 0;
-        cub::DeviceRadixSort::SortKeys(nullptr, pl.cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
-                                       (long long)C * pl.Emax, 0, 64);
-        pl.cub = o; o += al(pl.cub_bytes);
         pl.phic1 = o; o += al((size_t)pl.grid1 * pl.capP * (N > 1024 ? 16 : 8) * 4);
         pl.phic2 = o; o += al((size_t)pl.grid2 * pl.capP * 32 * 4);
         pl.pcr = o; o += al((size_t)pl.grid1 * pl.capP * 4);
@@ -879,7 +1013,7 @@ static bool make_plan(int B, int N, size_t ws_bytes, Plan& pl) {
 
 // W0 > 0: a narrow first tier (small clouds hold few classes at once: two mask words instead of eight
 // quarter the gathers and the shared memory of a visited edge); W1: the regular first tier; then W = 32
-template <int NTH, int APT, int W0, int W1>
+template <int NTH, int APT, int W0, int W1, typename TT>
 static cudaError_t launch_sweeps(Params p, const Plan& pl, char* w8, cudaStream_t st) {
     int* counters = (int*)(w8 + pl.counters);
     cudaError_t e;
@@ -890,10 +1024,10 @@ static cudaError_t launch_sweeps(Params p, const Plan& pl, char* w8, cudaStream_
         p.worklist = nullptr; p.n_work = nullptr;
         p.overflow_list = (int*)(w8 + pl.list0); p.n_overflow = counters + 1;
         const size_t smem = sweep_smem<WN>(p.N, false);
-        e = cudaFuncSetAttribute(sweep_kernel<NTH, APT, WN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(sweep_kernel<NTH, APT, WN, false, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         const int grid = p.C < pl.grid1 ? p.C : pl.grid1;
-        sweep_kernel<NTH, APT, WN, false><<<grid, NTH, smem, st>>>(p, 0);
+        sweep_kernel<NTH, APT, WN, false, TT><<<grid, NTH, smem, st>>>(p, 0);
         count_launch();
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -903,10 +1037,10 @@ static cudaError_t launch_sweeps(Params p, const Plan& pl, char* w8, cudaStream_
         p.worklist = W0 > 0 ? (const int*)(w8 + pl.list0) : nullptr; p.n_work = W0 > 0 ? counters + 1 : nullptr;
         p.overflow_list = (int*)(w8 + pl.list); p.n_overflow = counters;
         const size_t smem = sweep_smem<W1>(p.N, false);
-        e = cudaFuncSetAttribute(sweep_kernel<NTH, APT, W1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(sweep_kernel<NTH, APT, W1, false, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         const int grid = p.C < pl.grid1 ? p.C : pl.grid1;
-        sweep_kernel<NTH, APT, W1, false><<<grid, NTH, smem, st>>>(p, W0 > 0 ? 1 : 0);
+        sweep_kernel<NTH, APT, W1, false, TT><<<grid, NTH, smem, st>>>(p, W0 > 0 ? 1 : 0);
         count_launch();
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -918,10 +1052,10 @@ static cudaError_t launch_sweeps(Params p, const Plan& pl, char* w8, cudaStream_
         p.phic = (uint32_t*)(w8 + pl.phic2);
         constexpr bool SG = (APT > 4);
         const size_t smem = sweep_smem<32>(p.N, SG);
-        e = cudaFuncSetAttribute(sweep_kernel<NTH, APT, 32, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(sweep_kernel<NTH, APT, 32, SG, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         const int grid = p.C < pl.grid2 ? p.C : pl.grid2;
-        sweep_kernel<NTH, APT, 32, SG><<<grid, NTH, smem, st>>>(p, 1);
+        sweep_kernel<NTH, APT, 32, SG, TT><<<grid, NTH, smem, st>>>(p, 1);
         count_launch();
         e = cudaGetLastError();
     }
@@ -957,8 +1091,8 @@ extern "C" int tda_rips_h01_large(const float* D, const int* npts, int B, int N,
     p.bd0 = bd0; p.pr0 = pr0; p.bd1 = bd1; p.pr1 = pr1; p.counts = counts; p.status = status;
     p.cap0 = cap0; p.cap1 = cap1;
     p.ldT = pl.ldT; p.ib = pl.ib; p.Emax = pl.Emax;
-    p.keysA = (uint64_t*)(w8 + pl.keysA); p.keysB = (uint64_t*)(w8 + pl.keysB);
-    p.P = (uint32_t*)(w8 + pl.P); p.T = (uint32_t*)(w8 + pl.T); p.Q = (uint16_t*)(w8 + pl.Q);
+    p.sortbuf = (uint32_t*)(w8 + pl.sortbuf); p.skey = (uint32_t*)(w8 + pl.skey);
+    p.P = (uint32_t*)(w8 + pl.P); p.T = (void*)(w8 + pl.T); p.Q = (uint16_t*)(w8 + pl.Q);
     p.defv = (uint16_t*)(w8 + pl.defv); p.m = (int*)(w8 + pl.m); p.nanflag = (int*)(w8 + pl.nanflag);
     p.capP = pl.capP; p.capR = pl.capR;
     p.phic = nullptr; p.pcr = (uint32_t*)(w8 + pl.pcr); p.act = (uint32_t*)(w8 + pl.act);
@@ -969,34 +1103,17 @@ extern "C" int tda_rips_h01_large(const float* D, const int* npts, int B, int N,
         const int C = (B - c0) < pl.C ? (B - c0) : pl.C;
         p.c0 = c0; p.C = C;
         if ((e = cudaMemsetAsync(w8 + pl.counters, 0, 256, st)) != cudaSuccess) return (int)e;
-        if ((e = cudaMemsetAsync(p.m, 0, (size_t)C * 4, st)) != cudaSuccess) return (int)e;
-        if ((e = cudaMemsetAsync(p.nanflag, 0, (size_t)C * 4, st)) != cudaSuccess) return (int)e;
-        if ((e = cudaMemsetAsync(p.T, 0xFF, (size_t)C * N * pl.ldT * 4, st)) != cudaSuccess) return (int)e;
-        if ((e = cudaMemsetAsync(p.Q, 0, (size_t)C * N * pl.ldT * 2, st)) != cudaSuccess) return (int)e;
         {
-            ProfScope prof("rips_large_keys", st);
-            long long per = ((long long)N * N + 255) / 256;
-            dim3 grid((unsigned)(per < 1024 ? per : 1024), (unsigned)C);
-            keys_kernel<<<grid, 256, 0, st>>>(p);
-            count_launch();
-            if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
-        }
-        {
-            ProfScope prof("rips_large_sort", st);
-            size_t tb = pl.cub_bytes;
-            int cb = bits_for(C);
-            int end_bit = 32 + pl.ib + cb;
-            if (end_bit > 64) end_bit = 64;
-            e = cub::DeviceRadixSort::SortKeys((void*)(w8 + pl.cub), tb, (const uint64_t*)p.keysA, p.keysB,
-                                               (long long)C * pl.Emax, 0, end_bit, st);
-            count_launch(4);
-            if (e != cudaSuccess) return (int)e;
-        }
-        {
-            ProfScope prof("rips_large_scatter", st);
-            long long per = (pl.Emax + 255) / 256;
-            dim3 grid((unsigned)(per < 1024 ? per : 1024), (unsigned)C);
-            scatter_kernel<<<grid, 256, 0, st>>>(p);
+            // keys + per-CTA radix sort + rank matrix in one kernel (fills T, Q, m, nanflag of the chunk)
+            ProfScope prof("rips_large_rank", st);
+            const int grid = C < kSms ? C : kSms;
+            if (N <= 256) {
+                cudaFuncSetAttribute(rank_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRankSmem);
+                rank_kernel<uint16_t><<<grid, kRankThreads, kRankSmem, st>>>(p);
+            } else {
+                cudaFuncSetAttribute(rank_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRankSmem);
+                rank_kernel<uint32_t><<<grid, kRankThreads, kRankSmem, st>>>(p);
+            }
             count_launch();
             if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
         }
@@ -1011,17 +1128,18 @@ extern "C" int tda_rips_h01_large(const float* D, const int* npts, int B, int N,
             ProfScope prof("rips_large_classify", st);
             long long blocks = (pl.Emax * C + 255) / 256;
             if (blocks > 148 * 64) blocks = 148 * 64;
-            classify_kernel<<<(unsigned)blocks, 256, 0, st>>>(p);
+            if (N <= 256) classify_kernel<uint16_t><<<(unsigned)blocks, 256, 0, st>>>(p);
+            else classify_kernel<uint32_t><<<(unsigned)blocks, 256, 0, st>>>(p);
             count_launch();
             if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
         }
         // 256 threads whatever the size (block barriers are what a visited edge pays for), 1-8 apexes each
         // (small clouds: one or two warps per cloud, the visited edges are issue-bound there)
-        if (N <= 128) e = launch_sweeps<32, 4, 2, 8>(p, pl, w8, st);
-        else if (N <= 256) e = launch_sweeps<64, 4, 2, 8>(p, pl, w8, st);
-        else if (N <= 512) e = launch_sweeps<256, 2, 0, 8>(p, pl, w8, st);
-        else if (N <= 1024) e = launch_sweeps<256, 4, 0, 8>(p, pl, w8, st);
-        else e = launch_sweeps<256, 8, 0, 16>(p, pl, w8, st);
+        if (N <= 128) e = launch_sweeps<32, 4, 2, 8, uint16_t>(p, pl, w8, st);
+        else if (N <= 256) e = launch_sweeps<64, 4, 2, 8, uint16_t>(p, pl, w8, st);
+        else if (N <= 512) e = launch_sweeps<256, 2, 0, 8, uint32_t>(p, pl, w8, st);
+        else if (N <= 1024) e = launch_sweeps<256, 4, 0, 8, uint32_t>(p, pl, w8, st);
+        else e = launch_sweeps<256, 8, 0, 16, uint32_t>(p, pl, w8, st);
         if (e != cudaSuccess) return (int)e;
     }
     return 0;

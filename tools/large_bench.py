@@ -56,7 +56,7 @@ def main():
             _lib.profile_enable(True)
             rips_h01_batched(D, thr, cap1=cap1, want_pairs=True, out=out, engine=engine)
             torch.cuda.synchronize()
-            for k in ("keys", "sort", "scatter", "kruskal", "classify", "sweep_t0", "sweep_t1", "sweep_t2"):
+            for k in ("rank", "kruskal", "classify", "sweep_t0", "sweep_t1", "sweep_t2"):
                 parts[k] = round(_lib.profile_query("rips_large_" + k)[0], 3)
             _lib.profile_enable(False)
         c = out["counts"]
