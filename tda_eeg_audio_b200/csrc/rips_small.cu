@@ -63,8 +63,10 @@ template <int W, bool PHI_GLOBAL, int RSW = 0> struct Layout {
     // death records of the one-word tier live in a global scratch (written ~40 times per window): the
     // kilobyte this frees lets eight warps share a CTA, sixteen an SM
     static constexpr bool kRecGlobal = PHI_GLOBAL || W == 1;
-    static __host__ __device__ size_t tail(int N) {          // visit bitmap, brank, comp, eld
-        return a16((size_t)epad(N) / 8 + 32 * W * 2 + 2 * kMaxN);
+    // visit bitmap, brank, then comp + eld (Kruskal) overlaid by S, the per-vertex summary of the sweep
+    static __host__ __device__ size_t tail(int N) {
+        const size_t sv = (size_t)(RS ? N : kMaxN) * 4 * W, ce = 2 * kMaxN;
+        return a16((size_t)epad(N) / 8 + 32 * W * 2 + (sv > ce ? sv : ce));
     }
     // an SM has 228 KB of shared memory; every resident CTA also takes 1 KB of it
     static __host__ __device__ size_t budget() { return (size_t)(((228 * 1024) / 2 - 1024) / (RS ? RSW : 1)) & ~(size_t)15; }
@@ -95,7 +97,7 @@ template <int W, bool PHI_GLOBAL, int RSW = 0> struct Layout {
         s += kRecGlobal ? 0 : (size_t)recs(N) * 12;           // death records
         s += (size_t)epad(N) / 8;                             // visit bitmap
         s += 32 * W * 2;                                      // brank
-        s += 2 * kMaxN;                                       // comp, eld
+        s += (size_t)kMaxN * 4 * W > 2 * kMaxN ? (size_t)kMaxN * 4 * W : 2 * kMaxN;   // comp, eld | S
         return a16(s);
     }
 };
@@ -134,11 +136,14 @@ template <int W, bool PHI_GLOBAL, int NT, int RSW = 0> struct Warp {
     __device__ __forceinline__ uint16_t* brank() const { return (uint16_t*)(base + L::off_visit(n()) + (size_t)epad() / 8); }
     __device__ __forceinline__ uint8_t* comp() const { return base + L::off_visit(n()) + (size_t)epad() / 8 + 32 * W * 2; }
     __device__ __forceinline__ uint8_t* eld() const { return comp() + kMaxN; }
+    // S[v][W]: superset of the OR of PHI over the edges at vertex v (over comp / eld once Kruskal is done)
+    __device__ __forceinline__ uint32_t* S() const { return (uint32_t*)comp(); }
     __device__ __forceinline__ uint8_t* defv() const { return defv_g; }
     // ---- per-window uniform state
     uint32_t live[W], used[W];
     int n0, n1, ncomp, m;
     bool overflow;
+    bool s_changed;   // S gained bits since the sweep last evaluated which edges a live cocycle can see
 
     __device__ __forceinline__ float dist(int a, int b) const {
         return __ldg(Db + (d_rowoff(min(a, b), ld, n()) + max(a, b))) + 0.0f;
@@ -193,9 +198,18 @@ template <int W, bool PHI_GLOBAL, int NT, int RSW = 0> struct Warp {
         if (s < 0) return;
         if (lane == 0) {
             brank()[s] = (uint16_t)r;
+            const uint32_t pij = P()[r];
+            uint32_t* si = S() + p_i(pij) * W;
+            uint32_t* sj = S() + p_j(pij) * W;
 #pragma unroll
-            for (int w = 0; w < W; ++w) phi()[(size_t)r * W + w] = (w == (s >> 5)) ? (1u << (s & 31)) : 0u;
+            for (int w = 0; w < W; ++w) {
+                const uint32_t bit = (w == (s >> 5)) ? (1u << (s & 31)) : 0u;
+                phi()[(size_t)r * W + w] = bit;
+                si[w] |= bit;
+                sj[w] |= bit;
+            }
         }
+        s_changed = true;
         __syncwarp();
     }
 
@@ -269,10 +283,17 @@ template <int W, bool PHI_GLOBAL, int NT, int RSW = 0> struct Warp {
                 for (int q = (age & ~31) + lane; q < upto; q += 32) {
                     uint32_t* e = phi() + (size_t)q * W;
                     if (e[sw] & sb) {
+                        const uint32_t pq = P()[q];
+                        uint32_t* si = S() + p_i(pq) * W;
+                        uint32_t* sj = S() + p_j(pq) * W;
 #pragma unroll
-                        for (int w = 0; w < W; ++w) e[w] ^= cv[w];
+                        for (int w = 0; w < W; ++w) {
+                            e[w] ^= cv[w];
+                            if (cv[w]) { atomicOr(si + w, cv[w]); atomicOr(sj + w, cv[w]); }
+                        }
                     }
                 }
+                s_changed = true;
                 __syncwarp();
             }
         }
@@ -330,9 +351,21 @@ template <int W, bool PHI_GLOBAL, int NT, int RSW = 0> struct Warp {
 #pragma unroll
         for (int w = 0; w < W; ++w)
             xtop[w] = __shfl_sync(kFull, (vtop >> 5) ? c[1][w] : c[0][w], vtop & 31) & live[w];
-        if (lane == 0) {
+        uint32_t anyx = 0;
 #pragma unroll
-            for (int w = 0; w < W; ++w) phi()[(size_t)r * W + w] = xtop[w];
+        for (int w = 0; w < W; ++w) anyx |= xtop[w];
+        if (anyx) {   // (PHI[r] is zero already otherwise)
+            if (lane == 0) {
+                uint32_t* si = S() + i * W;
+                uint32_t* sj = S() + j * W;
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    phi()[(size_t)r * W + w] = xtop[w];
+                    si[w] |= xtop[w];
+                    sj[w] |= xtop[w];
+                }
+            }
+            s_changed = true;
         }
         uint32_t anyc = 0;
 #pragma unroll
@@ -683,6 +716,27 @@ template <int W, bool PHI_GLOBAL, int NT, int RSW = 0> struct Warp {
             }
         }
         __syncwarp();
+        // ---- H0 essentials: eldest vertex of every surviving component, ascending (written now: the
+        //      component arrays are about to become the sweep's vertex summary S; a window that a later
+        //      tier redoes simply writes them again)
+        {
+            int base = n0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int v = lane + 32 * h;
+                const bool is = v < n() && eld()[comp()[v]] == v;
+                const uint32_t bal = __ballot_sync(kFull, is);
+                if (is) {
+                    const size_t o = ((size_t)b * n() + base + __popc(bal & lanemask_lt())) * 2;
+                    p.bd0[o] = 0.0f;
+                    p.bd0[o + 1] = __int_as_float(0x7F800000);
+                    if (p.pr0) { p.pr0[o] = v; p.pr0[o + 1] = -1; }
+                }
+                base += __popc(bal);
+            }
+            n0 = base;
+        }
+        __syncwarp();
         // ---- rank matrix T (0xFFFF = edge absent) over region A
         {
             uint32_t* T32 = reinterpret_cast<uint32_t*>(T());
@@ -726,8 +780,10 @@ template <int W, bool PHI_GLOBAL, int NT, int RSW = 0> struct Warp {
                 if (lane == 0) visit()[k0 >> 5] = bal;
             }
         }
-        // ---- PHI := 0
+        // ---- PHI := 0, S := 0
         for (int q = lane; q < min(m, phicap()) * W; q += 32) phi()[q] = 0;
+        for (int q = lane; q < n() * W; q += 32) S()[q] = 0;
+        s_changed = false;
         __syncwarp();
         // ---- the sweep through the live spans
         {
@@ -746,18 +802,55 @@ template <int W, bool PHI_GLOBAL, int NT, int RSW = 0> struct Warp {
                     r = 32 * wq + __ffs(bits) - 1;
                     if (r >= mlim) break;
                 }
-                const uint32_t pij = P()[r];
-                if (pij & (kTie | kTiePrev)) {
-                    int r0 = r;
-                    while (r0 > 0 && (P()[r0 - 1] & kTie)) --r0;
-                    int r1 = r;
-                    while (P()[r1] & kTie) ++r1;
-                    ++r1;
-                    tie_run(r0, r1);
-                    r = r1;
-                } else {
-                    if (!(pij & kMst)) process_edge(r, fetch_edge(pij));
-                    ++r;
+                // ---- the 32 ranks of r's chunk at once: which of them can a live cocycle see?  A non-tied edge
+                //      that gives no birth and whose end points carry no live cocycle bit (S) keeps PHI = 0 and
+                //      has coboundary 0 on every triangle: it is not visited at all
+                const int rb = r & ~31, rr = rb + lane;
+                const uint32_t pl = rr < mlim ? P()[rr] : kMst;
+                const uint32_t vbits = visit()[rb >> 5];
+                auto hot_ranks = [&](int from) -> uint32_t {
+                    bool hot = false;
+                    if (rr >= from && !(pl & kMst)) {
+                        hot = (vbits >> lane) & 1u;   // births and tie-run members
+                        if (!hot) {
+                            const uint32_t* si = S() + p_i(pl) * W;
+                            const uint32_t* sj = S() + p_j(pl) * W;
+#pragma unroll
+                            for (int w = 0; w < W; ++w) hot |= ((si[w] | sj[w]) & live[w]) != 0;
+                        }
+                    }
+                    return __ballot_sync(kFull, hot);
+                };
+                uint32_t bal = hot_ranks(r);
+                s_changed = false;
+                r = min(rb + 32, mlim);   // unless something below says otherwise
+                while (bal) {
+                    const int src = __ffs(bal) - 1;
+                    const int re = rb + src;
+                    const uint32_t pij = __shfl_sync(kFull, pl, src);
+                    if (pij & (kTie | kTiePrev)) {
+                        int r0 = re;
+                        while (r0 > 0 && (P()[r0 - 1] & kTie)) --r0;
+                        int r1 = re;
+                        while (P()[r1] & kTie) ++r1;
+                        ++r1;
+                        tie_run(r0, r1);
+                        // a run defines PHI values wholesale: every vertex counts as touched from here on
+                        for (int q = lane; q < n() * W; q += 32) S()[q] = kFull;
+                        __syncwarp();
+                        r = r1;
+                        break;
+                    }
+                    process_edge(re, fetch_edge(pij));
+                    if (overflow) break;
+                    if (!live_any()) { r = re + 1; break; }
+                    if (s_changed) {   // S gained bits: later ranks of the chunk may have become visible
+                        __syncwarp();
+                        bal = hot_ranks(re + 1);
+                        s_changed = false;
+                    } else {
+                        bal &= bal - 1;
+                    }
                 }
             }
             if (mlim < m && !overflow && r < m) {
@@ -814,24 +907,6 @@ template <int W, bool PHI_GLOBAL, int NT, int RSW = 0> struct Warp {
             return;
         }
         __syncwarp();
-        // ---- H0 essentials: eldest vertex of every surviving component, ascending
-        {
-            int base = n0;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int v = lane + 32 * h;
-                const bool is = v < n() && eld()[comp()[v]] == v;
-                const uint32_t bal = __ballot_sync(kFull, is);
-                if (is) {
-                    const size_t o = ((size_t)b * n() + base + __popc(bal & lanemask_lt())) * 2;
-                    p.bd0[o] = 0.0f;
-                    p.bd0[o + 1] = __int_as_float(0x7F800000);
-                    if (p.pr0) { p.pr0[o] = v; p.pr0[o + 1] = -1; }
-                }
-                base += __popc(bal);
-            }
-            n0 = base;
-        }
         // ---- H1 rows in ripser's order: descending birth rank
         int st = nan_seen ? TDA_ST_NAN_INPUT : 0;
         for (int k = lane; k < n1; k += 32) {
