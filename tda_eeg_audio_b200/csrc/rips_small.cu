@@ -754,30 +754,43 @@ template <int W, bool PHI_GLOBAL, int NT, int RSW = 0> struct Warp {
             }
             __syncwarp();
         }
-        // ---- which edges can give birth to a real class: no apex at their own time
-        //      (packed u16 min over v of max(T()[i][v], T()[j][v]); tie-run members are always visited)
+        // ---- which edges can give birth to a real class: no apex at their own time.  Adjacency bit masks
+        //      (two words per vertex, in the free sort buffer) grow chunk by chunk: an edge whose end points
+        //      already share a neighbour among the edges of EARLIER chunks has an apex, which settles nearly
+        //      every edge once the graph is a few hundred edges dense; only the others take the exact test
+        //      (packed u16 min over v of max(T()[i][v], T()[j][v])).  Tie-run members are always visited.
         {
             const int nw2 = ldtv() / 2;
+            uint32_t* adj = K2();
+            for (int q = lane; q < 2 * n(); q += 32) adj[q] = 0;
+            __syncwarp();
             for (int k0 = 0; k0 < epad(); k0 += 32) {
                 const int r = k0 + lane;
-                bool vis = false;
-                if (r < m) {
-                    const uint32_t pij = P()[r];
-                    if (!(pij & kMst)) {
-                        const bool tied = (pij & (kTie | kTiePrev)) != 0;
-                        if (tied) vis = true;
-                        else {
-                            const uint32_t* Ti = reinterpret_cast<const uint32_t*>(T() + (p_i(pij)) * ldtv());
-                            const uint32_t* Tj = reinterpret_cast<const uint32_t*>(T() + (p_j(pij)) * ldtv());
-                            uint32_t mn = 0xFFFFFFFFu;
-                            for (int w = 0; w < nw2; ++w) mn = __vminu2(mn, __vmaxu2(Ti[w], Tj[w]));
-                            const uint32_t mm = min(mn & 0xFFFFu, mn >> 16);
-                            vis = mm > (uint32_t)r;
-                        }
+                const bool act = r < m;
+                const uint32_t pij = act ? P()[r] : 0u;
+                const int i = p_i(pij), j = p_j(pij);
+                bool vis = false, exact = false;
+                if (act && !(pij & kMst)) {
+                    if (pij & (kTie | kTiePrev)) vis = true;
+                    else exact = ((adj[2 * i] & adj[2 * j]) | (adj[2 * i + 1] & adj[2 * j + 1])) == 0;
+                }
+                if (__any_sync(kFull, exact)) {
+                    if (exact) {
+                        const uint32_t* Ti = reinterpret_cast<const uint32_t*>(T() + i * ldtv());
+                        const uint32_t* Tj = reinterpret_cast<const uint32_t*>(T() + j * ldtv());
+                        uint32_t mn = 0xFFFFFFFFu;
+                        for (int w = 0; w < nw2; ++w) mn = __vminu2(mn, __vmaxu2(Ti[w], Tj[w]));
+                        const uint32_t mm = min(mn & 0xFFFFu, mn >> 16);
+                        vis = mm > (uint32_t)r;
                     }
                 }
                 const uint32_t bal = __ballot_sync(kFull, vis);
                 if (lane == 0) visit()[k0 >> 5] = bal;
+                if (act) {
+                    atomicOr(adj + 2 * i + (j >> 5), 1u << (j & 31));
+                    atomicOr(adj + 2 * j + (i >> 5), 1u << (i & 31));
+                }
+                __syncwarp();
             }
         }
         // ---- PHI := 0, S := 0
