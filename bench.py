@@ -219,7 +219,7 @@ def secondary_workloads(dev, x_raw):
     return out
 
 
-def raw_eeg_workload(dev, x, rec_chunk=354):
+def raw_eeg_workload(dev, x, rec_chunk=None):
     """SURVEY.md §8(d) config (b) "end-to-end from raw EEG" for ALL the recordings of the batch: raw
     47-channel EEG (R, 47, 15000) float64, device-resident -> zero-phase band-pass into 5 bands ->
     60 windows -> correlation distances -> Rips H0+H1 -> features -> (R, 220) table.  CUDA events,

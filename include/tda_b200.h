@@ -89,7 +89,7 @@ int tda_rips_h01_batched(const float* D, int B, int N, int ld, long long strideB
  * clouds (edge keys, one device-wide radix sort, rank matrices, Kruskal, first-cofacet /
  * apparent-pair classification of every edge) followed by one CTA per cloud for the serial part
  * (cocycle sweep over the edges a live class can see).  The chunk size follows from `ws_bytes`;
- * tda_rips_h01_large_workspace_bytes returns a size that holds min(B, what fits 12 GB) clouds.
+ * tda_rips_h01_large_workspace_bytes returns a size that holds min(B, what fits 48 GB) clouds.
  * Replaces ripser(...) inside compute_audio_persistence, /root/reference/scripts/utils.py:131. */
 size_t tda_rips_h01_large_workspace_bytes(int B, int N);
 int tda_rips_h01_large(const float* D, const int* npts, int B, int N, int ld, long long strideB,

@@ -131,7 +131,8 @@ template <int FORM> __device__ __forceinline__ void load_coefficients(const Coef
 template <int FORM, int NC>
 __global__ void __launch_bounds__(kSeq * kMaxBands, 2) iir_forward_kernel(const double* __restrict__ x, double* __restrict__ mid,
                                                                           long long n_seq, long long T, long long x_stride,
-                                                                          int edge, const __grid_constant__ Coef cf) {
+                                                                          int edge, int* __restrict__ next_group,
+                                                                          const __grid_constant__ Coef cf) {
     extern __shared__ __align__(16) double iir_smem[];   // per warp: ring of kRing tiles [32 rows][kLdIn]
     const long long Text = T + 2LL * edge;
     const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, band = tid >> 5;
@@ -141,7 +142,10 @@ __global__ void __launch_bounds__(kSeq * kMaxBands, 2) iir_forward_kernel(const 
     const long long n_groups = (n_seq + kSeq - 1) / kSeq;
     double cr[kMaxSec * 6];
     load_coefficients<FORM>(cf, band, cr);
-    for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    // groups are handed out through a device counter (the first gridDim.x statically): CTAs that run
+    // ahead of the others take more of them, which keeps the last wave short
+    __shared__ int grp_next;
+    for (long long grp = blockIdx.x; grp < n_groups;) {
         const long long seq0 = grp * kSeq;
         const bool active = seq0 + lane < n_seq;
         const int rows_here = (int)(n_seq - seq0 < kSeq ? n_seq - seq0 : kSeq);
@@ -205,6 +209,10 @@ __global__ void __launch_bounds__(kSeq * kMaxBands, 2) iir_forward_kernel(const 
             }
             buf = buf + 1 == kRing ? 0 : buf + 1;
         }
+        __syncthreads();   // (the only CTA-wide barriers: two per group of 15,054 samples)
+        if (tid == 0) grp_next = (int)gridDim.x + atomicAdd(next_group, 1);
+        __syncthreads();
+        grp = grp_next;
     }
 }
 
@@ -216,6 +224,7 @@ constexpr int kLdB = kSeq + 2;   // row stride of a backward tile: rows stay 16-
 template <int FORM, int NC>
 __global__ void __launch_bounds__(kSeq * kMaxBands, 2) iir_backward_kernel(const double* __restrict__ mid, double* __restrict__ y,
                                                                            long long n_seq, long long T, int edge,
+                                                                           int* __restrict__ next_group,
                                                                            const __grid_constant__ Coef cf) {
     extern __shared__ __align__(16) double iir_smem[];   // per warp: ring of kRing tiles [16 time rows][kLdB]
     const long long Text = T + 2LL * edge;
@@ -226,7 +235,10 @@ __global__ void __launch_bounds__(kSeq * kMaxBands, 2) iir_backward_kernel(const
     const long long n_groups = (n_seq + kSeq - 1) / kSeq;
     double cr[kMaxSec * 6];
     load_coefficients<FORM>(cf, band, cr);
-    for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    // groups are handed out through a device counter (the first gridDim.x statically): CTAs that run
+    // ahead of the others take more of them, which keeps the last wave short
+    __shared__ int grp_next;
+    for (long long grp = blockIdx.x; grp < n_groups;) {
         const long long seq0 = grp * kSeq;
         const bool active = seq0 + lane < n_seq;
         const int rows_here = (int)(n_seq - seq0 < kSeq ? n_seq - seq0 : kSeq);
@@ -292,6 +304,10 @@ __global__ void __launch_bounds__(kSeq * kMaxBands, 2) iir_backward_kernel(const
             }
             buf = buf + 1 == kRing ? 0 : buf + 1;
         }
+        __syncthreads();   // (the only CTA-wide barriers: two per group of 15,054 samples)
+        if (tid == 0) grp_next = (int)gridDim.x + atomicAdd(next_group, 1);
+        __syncthreads();
+        grp = grp_next;
     }
 }
 
@@ -302,7 +318,7 @@ extern "C" size_t tda_filtfilt_workspace_bytes(long long n_seq, int n_bands, lon
     if (n_seq < 0 || n_bands < 1 || T < 1 || padlen < 0) return 0;
     // the padded intermediate, time-major per group of 32 sequences (the last group is padded to 32)
     const long long groups = (n_seq + tda::iir::kSeq - 1) / tda::iir::kSeq;
-    return (size_t)groups * tda::iir::kSeq * n_bands * (size_t)(T + 2LL * padlen) * sizeof(double);
+    return (size_t)groups * tda::iir::kSeq * n_bands * (size_t)(T + 2LL * padlen) * sizeof(double) + 256;   // + work counters
 }
 
 extern "C" int tda_filtfilt_f64(const double* x, long long n_seq, long long T, long long x_stride, int form,
@@ -353,6 +369,8 @@ extern "C" int tda_filtfilt_f64(const double* x, long long n_seq, long long T, l
     const int grid = (int)(groups < maxb ? groups : maxb);
     cudaStream_t st = (cudaStream_t)stream;
     double* mid = (double*)ws;
+    int* counters = (int*)((char*)ws + tda_filtfilt_workspace_bytes(n_seq, n_bands, T, padlen) - 256);
+    if (cudaError_t e0 = cudaMemsetAsync(counters, 0, 256, st); e0 != cudaSuccess) return (int)e0;
     // sections / taps known at compile time for the filters of the pipeline (order-4 band-pass: 4 sections
     // or 9 taps; order-4 low-pass: 5 taps); any other count runs the same kernels with a run-time count
     auto launch = [&](auto fwd, auto bwd) -> int {
@@ -360,14 +378,14 @@ extern "C" int tda_filtfilt_f64(const double* x, long long n_seq, long long T, l
         cudaFuncSetAttribute(bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b);
         {
             tda::ProfScope prof(form == 0 ? "iir_sos_forward" : "iir_ba_forward", st);
-            fwd<<<grid, nth, smem_f, st>>>(x, mid, n_seq, T, x_stride, padlen, cf);
+            fwd<<<grid, nth, smem_f, st>>>(x, mid, n_seq, T, x_stride, padlen, counters, cf);
             tda::count_launch();
         }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
         {
             tda::ProfScope prof(form == 0 ? "iir_sos_backward" : "iir_ba_backward", st);
-            bwd<<<grid, nth, smem_b, st>>>(mid, y, n_seq, T, padlen, cf);
+            bwd<<<grid, nth, smem_b, st>>>(mid, y, n_seq, T, padlen, counters + 1, cf);
             tda::count_launch();
         }
         return (int)cudaGetLastError();

@@ -1004,8 +1004,9 @@ static bool make_plan(int B, int N, size_t ws_bytes, Plan& pl) {
     };
     long long C = B < cmax ? B : cmax;
     if (C < 1) C = 1;
-    // sizing query (ws_bytes == 0): aim at <= 12 GB, at least one cloud
-    const size_t budget = ws_bytes ? ws_bytes : ((size_t)12 << 30);
+    // sizing query (ws_bytes == 0): aim at <= 48 GB of the 180 GB (big clouds are latency-bound per CTA: the
+    // more of them are resident at once, two per SM, the better), at least one cloud
+    const size_t budget = ws_bytes ? ws_bytes : ((size_t)48 << 30);
     layout((int)C);
     while (pl.total > budget && C > 1) { C = (C + 1) / 2; layout((int)C); }
     return ws_bytes == 0 || pl.total <= ws_bytes;

@@ -121,12 +121,20 @@ def corrdist_windows(x, win, step, method="euclidean", out=None, want_corr=False
 
 
 def eeg_distances_from_raw(x, fs=250, bands=FREQ_BANDS, window_size=1.0, overlap=0.75, order=4,
-                           rec_chunk=256, out=None):
+                           rec_chunk=None, out=None):
     """Raw EEG (R, C, T) CUDA float64 -> correlation-distance matrices (R, n_bands, W, C, C) float32:
     notebooks 1 + 2 of the reference for a whole dataset (band-pass sos filtfilt, 1 s windows,
-    corrcoef, sqrt(2(1-r)))."""
+    corrcoef, sqrt(2(1-r))).
+
+    rec_chunk: recordings filtered per launch (None: as many as fit half of the free device memory --
+    the filtered bands and the padded intermediate take 2 x n_bands x 8 bytes per sample; the filter
+    kernels hand out their work dynamically, so one big launch beats several small ones)."""
     import torch
     R, C, T = x.shape
+    if rec_chunk is None:
+        free, _ = torch.cuda.mem_get_info(x.device)
+        per_rec = 2 * len(bands) * C * (T + 64) * 8
+        rec_chunk = int(max(1, min(R, (free // 2) // per_rec)))
     win = int(window_size * fs)
     step = int(win * (1 - overlap))
     W = n_windows(T, win, step)

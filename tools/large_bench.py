@@ -39,7 +39,8 @@ def timed(fn, n=3, warm=1):
 
 
 CASES = [("large", 64, 1000, 2.0), ("large", 64, 1500, 2.0), ("large", 64, 2000, 2.0), ("large", 64, 2000, 0.25),
-         ("large", 296, 1000, 2.0), ("large", 8192, 124, 2.0), ("large", 8192, 248, 2.0)]
+         ("large", 296, 1000, 2.0), ("large", 148, 2000, 2.0), ("large", 296, 2000, 2.0), ("large", 444, 2000, 2.0),
+         ("large", 8192, 124, 2.0), ("large", 8192, 248, 2.0)]
 
 
 def main():

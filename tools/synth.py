@@ -54,7 +54,7 @@ def raw_eeg_to_device(rec0: int, n: int, device, T: int = T_EEG, chunk: int = 64
     return x
 
 
-def eeg_distance_matrices(rec0: int, n: int, device, step: int = 250, rec_chunk: int = 128, keep_raw: bool = False):
+def eeg_distance_matrices(rec0: int, n: int, device, step: int = 250, rec_chunk: int = 256, keep_raw: bool = False):
     """BASELINE §5(b) input: (n, 5, W, 47, 47) float32 correlation-distance matrices of recordings
     rec0 .. rec0+n-1 (5 bands, 1 s windows, W = 60 at step 250), built by the repo's own signal chain
     on the device.  Returns (D, x) with x the raw recordings when keep_raw."""
