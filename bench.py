@@ -153,10 +153,10 @@ def run_reference(args, rank, world):
     nrec = min(CPU_SAMPLE_RECORDINGS, args.recordings)
     B = nrec * N_BANDS * N_WIN
     cores = os.cpu_count() or 1
+    with mp.get_context("fork").Pool(min(cores, nrec)) as pool:      # (before any OpenMP runtime exists)
+        D = np.concatenate(pool.map(_cpu_distances_one, range(nrec))).reshape(B, N_CH, N_CH)
     from oracle import rips as orips
     orips.lib()
-    with mp.get_context("fork").Pool(min(cores, nrec)) as pool:
-        D = np.concatenate(pool.map(_cpu_distances_one, range(nrec))).reshape(B, N_CH, N_CH)
     for _ in range(args.warmup):
         orips.rips_h01_batched(D[: max(B // 10, 1)], THRESH, cap1=CAP1, nthreads=cores)
     t0 = time.perf_counter()

@@ -24,12 +24,14 @@
 //     statement): every live 1-cocycle is a bit ("slot") of a W-word mask stored per edge,
 //     PHI[rank].  The serial sweep only runs through the LIVE SPANS (from a birth until no class is
 //     alive); lanes are apexes, so the coboundary of ALL live cocycles on a triangle is two XORs
-//     per lane.  Apparent (zero-persistence) pairs cost nothing and take no slot.
+//     per lane.  Apparent (zero-persistence) pairs cost nothing and take no slot.  Inside a live span
+//     the sweep looks at 32 ranks at once: S[v] = OR of the cocycle masks over the edges at v, and an
+//     edge whose end points carry no live bit is not visited at all.
 //   * tie runs (equal float32 lengths) are replayed in the exact simplexwise order (all edges of
 //     the run, then the run's triangles in descending index, apparent pairs recognised inside the
 //     run) so that the persistence PAIRS, not only the diagrams, are bit-identical to Ripser's.
-//   * capacity tiers: W=1 (32 simultaneous classes, PHI for the first 604 ranks; 47-point windows
-//     only, where 99.95 % of the EEG windows fit) -> W=2 (64 classes, shared memory) -> W=4 ->
+//   * capacity tiers: W=1 (32 simultaneous classes, PHI for the first 588 ranks; 47-point windows
+//     only, where 99.93 % of the benchmark's EEG windows fit) -> W=2 (64 classes, shared memory) -> W=4 ->
 //     W=64 with PHI in a global scratch; a window that exceeds a tier is pushed on a device-side
 //     list and redone by the next tier, no host round-trip.
 #include <cuda_runtime.h>
@@ -47,7 +49,7 @@ namespace rips_small {
 // through registers, so the sort needs one key buffer and a payload ping-pong instead of two of each,
 // and the window gets a fixed budget of shared memory, 1 / (2 RSW) of an SM: [K | T] [P] [P2 + digit
 // counters | PHI] [visit, brank, comp, eld].  What is left for PHI after the other arrays sets phicap():
-// all 1,081 ranks at ten warps per CTA, 824 at eleven, 604 at twelve (a window with a class alive or
+// all 1,081 ranks at ten warps per CTA, 588 at twelve (a window with a class alive or
 // born beyond that rank is redone by the next tier; no EEG-like window of the benchmark is).
 template <int W, bool PHI_GLOBAL, int RSW = 0> struct Layout {
     static constexpr bool RS = RSW > 0;
