@@ -15,6 +15,16 @@
 // lives in the warp's shared memory in float64 (M <= N after an optional role swap), lanes stride
 // over the columns for the relax + arg-min step.  The optimum of an LSAP is unique in value, so
 // the result matches scipy's to rounding.
+//
+// H0 diagrams are one-dimensional: every birth is 0 and the deaths come sorted.  For such a pair (all
+// births of both diagrams equal, deaths non-decreasing -- checked per pair, anything else takes the
+// general solver) the ground costs have the Monge property, so an optimal matching does not cross and
+// the same optimum is the end of a dynamic programme over the two sorted lists,
+//   f[i][j] = min(f[i-1][j] + ds_i, f[i][j-1] + dt_j, f[i-1][j-1] + c_ij),
+// one row at a time with the lanes along j: f[i][j] = P_j + min_{k <= j}(g_k - P_k), P = prefix sums of
+// dt, g_k = min(f[i-1][k] + ds_i, f[i-1][k-1] + c_ik) -- a prefix minimum, i.e. a warp scan.  The c_ij
+// are the very same Gram-trick values.  46 x 113 cells instead of O(M^2 N) augmentation steps:
+// 19,200 EEG-vs-audio H0 pairs in 13.1 ms before (profiles/r02_wasserstein_h0_ncu.json).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -39,7 +49,7 @@ template <typename TIn> struct Params {
 
 __host__ __device__ inline size_t smem_bytes(int rows_cap, int cols_cap) {
     size_t s = 0;
-    s += (size_t)rows_cap * cols_cap * 8;          // cost block
+    s += ((size_t)rows_cap * cols_cap + 2) * 8;    // cost block (+ slack: a row of the 1-D programme has cols + 1 entries)
     s += (size_t)2 * (rows_cap + cols_cap) * 8;    // points S, T  (x, y)
     s += (size_t)(rows_cap + cols_cap) * 8;        // ds, dt
     s += (size_t)(rows_cap + 1) * 8;               // u
@@ -82,7 +92,7 @@ __global__ void __launch_bounds__(32) wasserstein_kernel(Params<TIn> p) {
     const int lane = threadIdx.x;
     const int RC = p.rows_cap, CC = p.cols_cap;
     double* cost = (double*)wsm;
-    double* PA = cost + (size_t)RC * CC;   // points of A, then points of B right behind them
+    double* PA = cost + (size_t)RC * CC + 2;   // points of A, then points of B right behind them
     double* dS = PA + 2 * (size_t)(RC + CC);
     double* dT = dS + RC;
     double* u = dT + CC;
@@ -112,6 +122,62 @@ __global__ void __launch_bounds__(32) wasserstein_kernel(Params<TIn> p) {
         for (int i = lane; i < M; i += 32) dS[i] = -S[2 * i] * sn + S[2 * i + 1] * cs;
         for (int j = lane; j < N; j += 32) dT[j] = -T[2 * j] * sn + T[2 * j + 1] * cs;
         __syncwarp();
+        // ---- one-dimensional pair (all births equal, deaths sorted)?  then the dynamic programme
+        {
+            const double b0 = S[0];
+            bool ok = true;
+            for (int i = lane; i < M; i += 32) ok &= S[2 * i] == b0 && (i == 0 || S[2 * i + 1] >= S[2 * i - 1]);
+            for (int j = lane; j < N; j += 32) ok &= T[2 * j] == b0 && (j == 0 || T[2 * j + 1] >= T[2 * j - 1]);
+            if (__all_sync(kFull, ok)) {
+                // v -> P (prefix sums of dt), minv / u-region -> the two rows of f
+                double* Pre = v;
+                double* prev = minv;
+                double* cur = cost;            // >= N + 1 doubles: rows_cap * cols_cap >= N, and one of slack below
+                const int N1 = N + 1;
+                if (lane == 0) {
+                    double run = 0.0;
+                    Pre[0] = 0.0;
+                    for (int j = 0; j < N; ++j) { run += dT[j]; Pre[j + 1] = run; }
+                }
+                __syncwarp();
+                for (int j = lane; j < N1; j += 32) prev[j] = Pre[j];   // f[0][j]: every point of T unmatched
+                __syncwarp();
+                const int bs = (N1 + 31) / 32;                 // columns per lane (a contiguous block)
+                const int j0 = lane * bs, j1 = min(N1, j0 + bs);
+                for (int i = 1; i <= M; ++i) {
+                    const double sx = S[2 * (i - 1)], sy = S[2 * (i - 1) + 1], da = dS[i - 1];
+                    const double ns = __dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy));
+                    double run = kInf;                         // prefix minimum of g_k - P_k inside the block
+                    for (int j = j0; j < j1; ++j) {
+                        double g = prev[j] + da;
+                        if (j >= 1) {
+                            const double tx = T[2 * (j - 1)], ty = T[2 * (j - 1) + 1];
+                            const double nt = __dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty));
+                            const double dot = fma(sy, ty, __dmul_rn(sx, tx));
+                            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(-2.0, dot), ns), nt);
+                            g = fmin(g, prev[j - 1] + sqrt(fmax(d2, 0.0)));
+                        }
+                        run = fmin(run, g - Pre[j]);
+                        cur[j] = run;                          // block-local prefix minimum for now
+                    }
+                    // exclusive prefix minimum of the block minima over the lanes
+                    double carry = run;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const double y = __shfl_up_sync(kFull, carry, o);
+                        if (lane >= o) carry = fmin(carry, y);
+                    }
+                    carry = __shfl_up_sync(kFull, carry, 1);
+                    if (lane == 0) carry = kInf;
+                    for (int j = j0; j < j1; ++j) cur[j] = fmin(cur[j], carry) + Pre[j];
+                    __syncwarp();
+                    double* t = prev; prev = cur; cur = t;
+                }
+                if (lane == 0) p.out[k] = prev[N];
+                __syncwarp();
+                continue;
+            }
+        }
         // L2 costs with sklearn's Gram trick: sqrt(max(|s|^2 - 2 s.t + |t|^2, 0))
         for (int e = lane; e < M * N; e += 32) {
             const int i = e / N, j = e % N;

@@ -61,3 +61,39 @@ def test_properties_and_dropins(cuda):
     assert abs(wasserstein(lone, np.zeros((0, 2))) - 0.6 / np.sqrt(2)) < 1e-7     # to the diagonal
     assert safe_wasserstein(np.array([[0.0, np.inf]]), np.array([[0.0, np.inf]])) == 0.0
     assert safe_wasserstein(np.zeros(3), d2) == safe_wasserstein(np.zeros((0, 2)), d2)   # bad shape -> [[0,0]]
+
+
+def test_one_dimensional_pairs_take_the_dynamic_programme_and_agree(cuda):
+    """H0-shaped pairs (all births 0, deaths sorted) go through the 1-D dynamic programme, anything
+    else through the general solver: both against scipy's LSAP on persim's cost matrix, including
+    coincident deaths, duplicates, a shuffled copy (general solver on the same multiset) and births
+    that are equal but not zero."""
+    import torch
+    from oracle import wasserstein_ref
+    from tda_eeg_audio_b200.wasserstein import wasserstein_batched
+    rng = np.random.default_rng(5)
+    K, capA, capB = 48, 47, 250
+    A = np.zeros((K, capA, 2), np.float32); B = np.zeros((K, capB, 2), np.float32)
+    nA = rng.integers(1, capA + 1, K).astype(np.int32); nB = rng.integers(1, capB + 1, K).astype(np.int32)
+    for k in range(K):
+        a = np.sort(rng.random(nA[k])).astype(np.float32) * 1.4
+        b = np.sort(rng.random(nB[k])).astype(np.float32) * (0.2 if k % 2 else 1.4)
+        if k % 5 == 0 and nB[k] >= nA[k]:
+            b[: nA[k]] = a                      # coincident deaths: zero-cost matches, Gram-trick noise
+            b.sort()
+        if k % 7 == 0:
+            a[: len(a) // 2] = a[0]             # duplicates
+        A[k, :nA[k], 1] = a; B[k, :nB[k], 1] = b
+        if k % 11 == 0:
+            A[k, :nA[k], 0] = 0.25; B[k, :nB[k], 0] = 0.25; A[k, :nA[k], 1] += 0.25; B[k, :nB[k], 1] += 0.25
+    tA, tnA, tB, tnB = (torch.from_numpy(x).cuda() for x in (A, nA, B, nB))
+    got = wasserstein_batched(tA, tnA, tB, tnB).cpu().numpy()
+    perm = [rng.permutation(nA[k]) for k in range(K)]
+    A2 = A.copy()
+    for k in range(K):
+        A2[k, :nA[k]] = A[k, perm[k]]           # same multiset, unsorted -> the general solver
+    got2 = wasserstein_batched(torch.from_numpy(A2).cuda(), tnA, tB, tnB).cpu().numpy()
+    for k in range(K):
+        want = wasserstein_ref.wasserstein(A[k, :nA[k]].astype(np.float64), B[k, :nB[k]].astype(np.float64))
+        assert abs(got[k] - want) <= 1e-9 * max(1.0, abs(want)), (k, got[k], want)
+        assert abs(got2[k] - want) <= 1e-9 * max(1.0, abs(want)), (k, got2[k], want)
