@@ -306,6 +306,7 @@ __global__ void __launch_bounds__(kRankThreads, 1) rank_kernel(Params p) {
 template <int NTH> __device__ __forceinline__ int block_min(int v, int* sm) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     v = __reduce_min_sync(kFull, v);
+    if (NTH == 32) return v;   // a one-warp CTA: the warp reduction is the block reduction
     if (lane == 0) sm[warp] = v;
     __syncthreads();
     int x = lane < NTH / 32 ? sm[lane] : 0x7FFFFFFF;
@@ -316,6 +317,7 @@ template <int NTH> __device__ __forceinline__ int block_min(int v, int* sm) {
 template <int NTH> __device__ __forceinline__ uint32_t block_max_u32(uint32_t v, uint32_t* sm) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     v = __reduce_max_sync(kFull, v);
+    if (NTH == 32) return v;
     if (lane == 0) sm[warp] = v;
     __syncthreads();
     uint32_t x = lane < NTH / 32 ? sm[lane] : 0u;
@@ -725,11 +727,29 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
         const uint16_t* Qy = Q + (size_t)y * ldT;
         uint32_t ta[APT], tb[APT];
         int qa[APT], qb[APT];
+        // apex of (thread, h): four CONSECUTIVE apexes per thread when the ranks are 16-bit (clouds up to
+        // 256 points: NTH * 4 covers the padded row), so each of the four rows is one 8-byte load per thread;
+        // the padding of a row is "absent" in T and 0 in Q (rank_kernel), no bounds test needed
+        constexpr bool kVec = sizeof(TT) == 2 && APT == 4;
+        if constexpr (kVec) {
+            uint2 a = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu), b = a, qx = make_uint2(0u, 0u), qy = qx;
+            if (4 * tid < ldT) {
+                a = __ldg(reinterpret_cast<const uint2*>(Tx) + tid);
+                b = __ldg(reinterpret_cast<const uint2*>(Ty) + tid);
+                qx = reinterpret_cast<const uint2*>(Qx)[tid];
+                qy = reinterpret_cast<const uint2*>(Qy)[tid];
+            }
+            ta[0] = a.x & 0xFFFFu; ta[1] = a.x >> 16; ta[2] = a.y & 0xFFFFu; ta[3] = a.y >> 16;
+            tb[0] = b.x & 0xFFFFu; tb[1] = b.x >> 16; tb[2] = b.y & 0xFFFFu; tb[3] = b.y >> 16;
+            qa[0] = qx.x & 0xFFFFu; qa[1] = qx.x >> 16; qa[2] = qx.y & 0xFFFFu; qa[3] = qx.y >> 16;
+            qb[0] = qy.x & 0xFFFFu; qb[1] = qy.x >> 16; qb[2] = qy.y & 0xFFFFu; qb[3] = qy.y >> 16;
+        } else {
 #pragma unroll
-        for (int h = 0; h < APT; ++h) {
-            const int z = tid + h * NTH;
-            ta[h] = kAbsent; tb[h] = kAbsent; qa[h] = 0; qb[h] = 0;
-            if (z < n) { ta[h] = __ldg(Tx + z); tb[h] = __ldg(Ty + z); qa[h] = Qx[z]; qb[h] = Qy[z]; }
+            for (int h = 0; h < APT; ++h) {
+                const int z = tid + h * NTH;
+                ta[h] = kAbsent; tb[h] = kAbsent; qa[h] = 0; qb[h] = 0;
+                if (z < n) { ta[h] = __ldg(Tx + z); tb[h] = __ldg(Ty + z); qa[h] = Qx[z]; qb[h] = Qy[z]; }
+            }
         }
         if (warp == 0) {
             if (lane == 0) ctl[1] = 0;
@@ -753,7 +773,7 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
                     if (qb[h]) v ^= phic[(size_t)(qb[h] - 1) * W + w];
                     any |= v & live[w];
                 }
-                if (any) best = max(best, tri_index(x, y, tid + h * NTH) + 1u);
+                if (any) best = max(best, tri_index(x, y, kVec ? 4 * tid + h : tid + h * NTH) + 1u);
             }
         }
         const uint32_t top = block_max_u32<NTH>(best, red);
