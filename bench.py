@@ -203,7 +203,10 @@ def secondary_workloads(dev, x_raw):
     from tools.large_bench import takens_clouds
     out = {}
     for name, B, n in (("audio_takens_124pt", 8192, 124), ("audio_takens_248pt", 4096, 248),
-                       ("stress_1000pt", 296, 1000), ("stress_2000pt", 148, 2000)):
+                       ("stress_1000pt", 296, 1000), ("stress_2000pt", 148, 2000),
+                       # bigger batches: the sweep of a cloud is serial and a few clouds of a batch take several
+                       # times the mean, so the device-side queue has something to balance
+                       ("stress_1000pt_1184clouds", 1184, 1000), ("stress_2000pt_592clouds", 592, 2000)):
         D = takens_clouds(B, n, dev=dev)
         buf = {}
         ms = timed_ms(lambda: rips_h01_batched(D, THRESH, cap1=4 * n, want_pairs=False, out=buf, engine="large"))

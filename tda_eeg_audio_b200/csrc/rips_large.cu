@@ -67,9 +67,12 @@ __device__ __forceinline__ uint32_t float_key(float d) {
     uint32_t u = __float_as_uint(d);
     return (u >> 31) ? ~u : (u | 0x80000000u);
 }
+// (32-bit throughout: C(a,2) (a - 2) < 2^32 for a <= 2047 and is divisible by 3.  For a fixed edge (x, y) the
+// index grows with the apex z, so "largest index" = "largest apex" and one evaluation per edge is enough)
 __device__ __forceinline__ uint32_t tri_index(int x, int y, int z) {
-    const int a = max(x, max(y, z)), c = min(x, min(y, z)), b = x + y + z - a - c;
-    return (uint32_t)(c3(a) + c2(b) + c);
+    const uint32_t a = (uint32_t)max(x, max(y, z)), c = (uint32_t)min(x, min(y, z)), b = (uint32_t)(x + y + z) - a - c;
+    const uint32_t a2 = a * (a - 1u) / 2u;
+    return a2 * (a - 2u) / 3u + b * (b - 1u) / 2u + c;
 }
 
 struct Params {
@@ -108,6 +111,11 @@ struct Params {
     const int* n_work;
     int* overflow_list;
     int* n_overflow;
+    // sweep CTAs take their clouds from a device-side queue: a cloud's sweep is serial and its length varies
+    // several-fold between clouds, so a static assignment leaves most SMs idle behind the heaviest one
+    int* queue;         // next position of the current sweep launch
+    const int* order;   // position -> cloud, heaviest first (nullptr: positions are clouds)
+    int* nbirth;        // [C] number of H1 births of every cloud (classify), the weight behind `order`
 };
 
 __device__ __forceinline__ int cloud_n(const Params& p, int b) {
@@ -452,9 +460,23 @@ __global__ void __launch_bounds__(256) classify_kernel(Params p) {
                 }
             }
         }
-        if (dv < 0) Pc[r] = q | kBirth;
+        if (dv < 0) { Pc[r] = q | kBirth; atomicAdd(p.nbirth + c, 1); }
         else p.defv[(size_t)c * p.Emax + r] = (uint16_t)dv;
     }
+}
+
+// longest-processing-time-first order of the sweep queue: position of a cloud = number of clouds with more
+// births (ties: smaller index first).  The number of visited edges of a sweep grows with the births.
+__global__ void __launch_bounds__(256) order_kernel(Params p, int* order) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.C) return;
+    const int mine = p.nbirth[c];
+    int pos = 0;
+    for (int o = 0; o < p.C; ++o) {
+        const int nb = __ldg(p.nbirth + o);
+        pos += (nb > mine) || (nb == mine && o < c);
+    }
+    order[pos] = c;
 }
 
 // ------------------------------------------------------------------------------------ K5 sweep
@@ -466,6 +488,7 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
     uint32_t* live;   // [W]
     uint32_t* used;   // [W]
     uint32_t* brank;  // [32 W]
+    uint32_t* bstart; // [32 W] number of compact entries when the class of a slot was born
     uint32_t* cv;     // [W] broadcast of the firing mask
     uint32_t* peval;  // [W] value of the edge handled by the fast path
     uint32_t* pub;    // [4] published edge words
@@ -543,7 +566,7 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
             const int sb = __ffs(fw) - 1;
             val = (lane == sw) ? (1u << sb) : 0u;
             if (lane == sw) { used[lane] |= 1u << sb; live[lane] |= 1u << sb; }
-            if (lane == 0) brank[32 * sw + sb] = (uint32_t)pr;
+            if (lane == 0) { brank[32 * sw + sb] = (uint32_t)pr; bstart[32 * sw + sb] = (uint32_t)ctl[0]; }
             __syncwarp();
         } else {
             const uint32_t t = lane < W ? (S[(size_t)x * W + lane] | S[(size_t)y * W + lane]) & live[lane] : 0u;
@@ -583,63 +606,106 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
         if (tid < W) used[tid] = live[tid];
         __syncthreads();
     }
-    // coboundary mask of the live cocycles on triangle (x, y, z), given the value pe[] on (x, y)
-    __device__ __forceinline__ bool cob(const uint32_t (&pe)[W], int x, int y, int z, uint32_t (&c)[W]) const {
-        const int qa = Q[(size_t)x * ldT + z], qb = Q[(size_t)y * ldT + z];
+    // o ^= compact entry idx (a mask of W words = 8 W bytes, aligned: 16-byte loads)
+    __device__ __forceinline__ void xor_entry(int idx, uint32_t (&o)[W]) const {
+        if constexpr (W % 4 == 0) {
+            const uint4* e = reinterpret_cast<const uint4*>(phic + (size_t)idx * W);
+#pragma unroll
+            for (int w = 0; w < W / 4; ++w) {
+                const uint4 t = e[w];
+                o[4 * w] ^= t.x; o[4 * w + 1] ^= t.y; o[4 * w + 2] ^= t.z; o[4 * w + 3] ^= t.w;
+            }
+        } else {
+            const uint2* e = reinterpret_cast<const uint2*>(phic + (size_t)idx * W);
+#pragma unroll
+            for (int w = 0; w < W / 2; ++w) {
+                const uint2 t = e[w];
+                o[2 * w] ^= t.x; o[2 * w + 1] ^= t.y;
+            }
+        }
+    }
+    // coboundary mask of the live cocycles on triangle (x, y, z), given the value pe[] on (x, y) and the
+    // compact indices qa, qb of (x, z), (y, z)
+    __device__ __forceinline__ bool cob(const uint32_t (&pe)[W], int qa, int qb, uint32_t (&c)[W]) const {
+#pragma unroll
+        for (int w = 0; w < W; ++w) c[w] = pe[w];
+        if (qa) xor_entry(qa - 1, c);
+        if (qb) xor_entry(qb - 1, c);
         uint32_t any = 0;
 #pragma unroll
-        for (int w = 0; w < W; ++w) {
-            uint32_t v = pe[w];
-            if (qa) v ^= phic[(size_t)(qa - 1) * W + w];
-            if (qb) v ^= phic[(size_t)(qb - 1) * W + w];
-            v &= live[w];
-            c[w] = v;
-            any |= v;
-        }
+        for (int w = 0; w < W; ++w) { c[w] &= live[w]; any |= c[w]; }
         return any != 0;
     }
-    __device__ void load_pe(int x, int y, uint32_t (&pe)[W]) const {
+    // value of edge (x, y), masked by the live classes; false if it is zero
+    __device__ __forceinline__ bool load_pe(int x, int y, uint32_t (&pe)[W]) const {
         const int q = Q[(size_t)x * ldT + y];
 #pragma unroll
-        for (int w = 0; w < W; ++w) pe[w] = q ? phic[(size_t)(q - 1) * W + w] : 0u;
+        for (int w = 0; w < W; ++w) pe[w] = 0u;
+        if (!q) return false;
+        xor_entry(q - 1, pe);
+        uint32_t any = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) { pe[w] &= live[w]; any |= pe[w]; }
+        return any != 0;
     }
-    // death loop over the visited edges act[0 .. na)
-    __device__ void step_b(int r0, int r1) {
+    // death loop over the visited edges act[0 .. na); (spr, spq): rank and P word when the run is one edge
+    __device__ void step_b(int r0, int r1, int spr = -1, uint32_t spq = 0u) {
         const int na = ctl[1];
         while (true) {
-            uint32_t best = 0;
-            int best_a = -1, best_z = -1;
+            uint32_t best = 0, best_pq = 0;
+            int best_pr = -1, best_z = -1;
             for (int a = 0; a < na; ++a) {
-                const int pr = (int)act[a];
-                const uint32_t pq = __ldg(P + pr);
+                const int pr = spr >= 0 ? spr : (int)act[a];
+                const uint32_t pq = spr >= 0 ? spq : __ldg(P + pr);
                 const int x = p_i(pq), y = p_j(pq);
-                uint32_t pe[W];
-                load_pe(x, y, pe);
                 const TT* Tx = T + (size_t)x * ldT;
                 const TT* Ty = T + (size_t)y * ldT;
+                const uint16_t* Qx = Q + (size_t)x * ldT;
+                const uint16_t* Qy = Q + (size_t)y * ldT;
+                // every load of the scan that does not depend on another one is issued first: the scan is a
+                // chain of global round trips otherwise (rank -> index -> compact entry, per apex)
+                const int qe = Qx[y];
+                uint32_t ta[APT], tb[APT], qq[APT];
+#pragma unroll
+                for (int h = 0; h < APT; ++h) {
+                    const int z = tid + h * NTH;
+                    ta[h] = kAbsent; tb[h] = kAbsent; qq[h] = 0u;
+                    if (z < n) { ta[h] = __ldg(Tx + z); tb[h] = __ldg(Ty + z); qq[h] = (uint32_t)Qx[z] | ((uint32_t)Qy[z] << 16); }
+                }
+                uint32_t pe[W];
+#pragma unroll
+                for (int w = 0; w < W; ++w) pe[w] = 0u;
+                if (qe) xor_entry(qe - 1, pe);
+                uint32_t pany = 0;
+#pragma unroll
+                for (int w = 0; w < W; ++w) { pe[w] &= live[w]; pany |= pe[w]; }
+                // this thread's apexes from the largest down: the first triangle with a non-zero mask is its
+                // candidate for this edge (the index grows with the apex)
+                int zhit = -1;
 #pragma unroll
                 for (int h = APT - 1; h >= 0; --h) {
-                    const int z = tid + h * NTH;
-                    if (z < n && (uint32_t)__ldg(Tx + z) < (uint32_t)pr && (uint32_t)__ldg(Ty + z) < (uint32_t)pr) {
-                        uint32_t c[W];
-                        if (cob(pe, x, y, z, c)) {
-                            const uint32_t t = tri_index(x, y, z) + 1u;
-                            if (t > best) { best = t; best_a = a; best_z = z; }
-                        }
+                    if (zhit < 0 && ta[h] < (uint32_t)pr && tb[h] < (uint32_t)pr) {
+                        if (qq[h]) {
+                            uint32_t c[W];
+                            if (cob(pe, (int)(qq[h] & 0xFFFFu), (int)(qq[h] >> 16), c)) zhit = tid + h * NTH;
+                        } else if (pany) zhit = tid + h * NTH;   // both other edges carry 0: the mask is the edge's own value
                     }
+                }
+                if (zhit >= 0) {
+                    const uint32_t t = tri_index(x, y, zhit) + 1u;
+                    if (t > best) { best = t; best_pr = pr; best_pq = pq; best_z = zhit; }
                 }
             }
             const uint32_t top = block_max_u32<NTH>(best, red);
             if (top == 0) return;
-            if (best == top) {
-                const int pr = (int)act[best_a];
-                const uint32_t pq = __ldg(P + pr);
+            if (best == top) {   // the winner publishes its mask (recomputed: keeping it would cost W registers)
                 uint32_t pe[W], c[W];
-                load_pe(p_i(pq), p_j(pq), pe);
-                cob(pe, p_i(pq), p_j(pq), best_z, c);
+                const int x = p_i(best_pq), y = p_j(best_pq);
+                load_pe(x, y, pe);
+                cob(pe, Q[(size_t)x * ldT + best_z], Q[(size_t)y * ldT + best_z], c);
 #pragma unroll
                 for (int w = 0; w < W; ++w) cv[w] = c[w];
-                ctl[5] = pr;
+                ctl[5] = best_pr;
             }
             __syncthreads();
             // youngest class of the mask dies
@@ -671,19 +737,38 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
                 live[sw] &= ~sb;
             }
             if (others) {
+                // the dying cocycle vanishes on every edge older than its birth, and the compact entries are in
+                // rank order: only the entries from its birth on can carry its bit (it is the YOUNGEST class of
+                // the mask, so this is usually a short tail of the store)
                 const int npc = ctl[0];
-                for (int q = tid; q < npc; q += NTH) {
-                    uint32_t* e = phic + (size_t)q * W;
-                    if (e[sw] & sb) {
-                        const uint32_t pq = __ldg(P + pcr[q]);
-                        const int x = p_i(pq), y = p_j(pq);
+                const int q0 = (int)bstart[slot];
+                for (int qb = q0 + tid; qb < npc; qb += 4 * NTH) {
+                    uint32_t wd[4];
 #pragma unroll
-                        for (int w = 0; w < W; ++w) {
-                            const uint32_t v = cv[w];
-                            if (v) {
-                                e[w] ^= v;
-                                atomicOr(S + (size_t)x * W + w, v);
-                                atomicOr(S + (size_t)y * W + w, v);
+                    for (int u = 0; u < 4; ++u) {
+                        const int q = qb + u * NTH;
+                        wd[u] = q < npc ? phic[(size_t)q * W + sw] : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (wd[u] & sb) {
+                            const int q = qb + u * NTH;
+                            uint32_t* e = phic + (size_t)q * W;
+                            const uint32_t pq = __ldg(P + pcr[q]);
+                            const int x = p_i(pq), y = p_j(pq);
+#pragma unroll
+                            for (int w = 0; w < W; ++w) {
+                                const uint32_t v = cv[w];
+                                if (v) {
+                                    e[w] ^= v;
+                                    // (the supports of cocycles are fans around a few vertices: nearly every
+                                    // update finds the bits set already, and an atomic on a word that
+                                    // hundreds of threads hit serialises)
+                                    uint32_t* sx = S + (size_t)x * W + w;
+                                    uint32_t* sy = S + (size_t)y * W + w;
+                                    if ((*(volatile uint32_t*)sx & v) != v) atomicOr(sx, v);
+                                    if ((*(volatile uint32_t*)sy & v) != v) atomicOr(sy, v);
+                                }
                             }
                         }
                     }
@@ -761,24 +846,23 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
         const int code = ctl[6];
         if (code == 0 || ctl[3]) return;
         if (code == 2) { generic_run(pr, pr + 1); return; }
+        // does any triangle over the edge carry a non-zero mask?  (peval is masked by live already)
+        uint32_t pv[W], pany = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) { pv[w] = peval[w]; pany |= pv[w]; }
         uint32_t best = 0;
 #pragma unroll
         for (int h = 0; h < APT; ++h) {
             if (ta[h] < (uint32_t)pr && tb[h] < (uint32_t)pr) {
-                uint32_t any = 0;
-#pragma unroll
-                for (int w = 0; w < W; ++w) {
-                    uint32_t v = peval[w];
-                    if (qa[h]) v ^= phic[(size_t)(qa[h] - 1) * W + w];
-                    if (qb[h]) v ^= phic[(size_t)(qb[h] - 1) * W + w];
-                    any |= v & live[w];
-                }
-                if (any) best = max(best, tri_index(x, y, kVec ? 4 * tid + h : tid + h * NTH) + 1u);
+                if (qa[h] | qb[h]) {
+                    uint32_t c[W];
+                    if (cob(pv, qa[h], qb[h], c)) best = 1u;
+                } else if (pany) best = 1u;
             }
         }
         const uint32_t top = block_max_u32<NTH>(best, red);
         if (top == 0) return;
-        step_b(pr, pr + 1);
+        step_b(pr, pr + 1, pr, pe);
     }
 
     __device__ void run(const Params& p, int c, bool rezero_q) {
@@ -815,14 +899,17 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
         if (tid < 8) ctl[tid] = 0;
         __syncthreads();
         int rbase = 0;
+        uint32_t pe = kMst, pe_nx = kMst;
+        int dv = 0, dv_nx = 0;
+        if (tid < m) { pe = __ldg(P + tid); dv = defv[tid]; }
         while (rbase < m && !ctl[3]) {
-            // ---- this thread's edge of the chunk stays in registers while the chunk is scanned
+            // ---- this thread's edge of the chunk stays in registers while the chunk is scanned; the words of
+            //      the next chunk are on their way meanwhile (defv of a merging edge or a birth is never used)
             const int rr = rbase + tid;
-            uint32_t pe = kMst;
-            int dv = 0;
-            if (rr < m) {
-                pe = __ldg(P + rr);
-                if (!(pe & (kMst | kBirth))) dv = defv[rr];
+            {
+                const int rn = rr + NTH;
+                pe_nx = kMst; dv_nx = 0;
+                if (rn < m) { pe_nx = __ldg(P + rn); dv_nx = defv[rn]; }
             }
             const int rend = min(rbase + NTH, m);
             int done = rbase;
@@ -852,7 +939,13 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
                 done = r1;
                 if (done >= rend || ctl[3]) break;
             }
-            rbase = max(rbase + NTH, done);
+            if (done <= rbase + NTH) {
+                rbase += NTH; pe = pe_nx; dv = dv_nx;
+            } else {   // a tie run reached beyond the chunk
+                rbase = done;
+                pe = kMst; dv = 0;
+                if (rbase + tid < m) { pe = __ldg(P + rbase + tid); dv = defv[rbase + tid]; }
+            }
         }
         __syncthreads();
         const bool overflow = ctl[3] != 0;
@@ -930,6 +1023,7 @@ __global__ void __launch_bounds__(NTH) sweep_kernel(Params p, int rezero_q) {
     s.live = base;           base += W;
     s.used = base;           base += W;
     s.brank = base;          base += 32 * W;
+    s.bstart = base;         base += 32 * W;
     s.cv = base;             base += W;
     s.peval = base;          base += W;
     s.pub = base;            base += 4;
@@ -946,15 +1040,21 @@ __global__ void __launch_bounds__(NTH) sweep_kernel(Params p, int rezero_q) {
     s.lane = threadIdx.x & 31;
     s.warp = threadIdx.x >> 5;
     const int total = p.worklist ? *p.n_work : p.C;
-    for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const int c = p.worklist ? p.worklist[t] : t;
+    __shared__ int next_pos;
+    while (true) {
+        if (threadIdx.x == 0) next_pos = atomicAdd(p.queue, 1);
+        __syncthreads();
+        const int t = next_pos;
+        __syncthreads();
+        if (t >= total) break;
+        const int c = p.worklist ? p.worklist[t] : (p.order ? p.order[t] : t);
         s.run(p, c, rezero_q != 0);
         __syncthreads();
     }
 }
 
 template <int W> static size_t sweep_smem(int N, bool sg) {
-    size_t words = kMaxN / 32 + W + W + 32 * W + W + W + 4 + 34 + 8;
+    size_t words = kMaxN / 32 + W + W + 32 * W + 32 * W + W + W + 4 + 34 + 8;
     if (!sg) words += (size_t)N * W;
     return words * 4;
 }
@@ -964,7 +1064,7 @@ struct Plan {
     int N, ldT, ib, C, grid1, grid2, nth, apt, capP, capR;
     long long Emax;
     int tbytes;   // bytes per rank of T: 2 up to 256 points, else 4
-    size_t sortbuf, skey, P, T, Q, defv, m, nanflag, counters, list, list0, phic1, phic2, pcr, act, rec, sglob, total;
+    size_t sortbuf, skey, P, T, Q, defv, m, nanflag, counters, nbirth, order, list, list0, phic1, phic2, pcr, act, rec, sglob, total;
 };
 static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 static int bits_for(long long v) { int b = 1; while ((1ll << b) < v) ++b; return b; }
@@ -978,6 +1078,7 @@ static int tier1_ctas_per_sm(int N, int nth) {
     int by_smem = (int)((227 * 1024) / ((N > 1024 ? sweep_smem<16>(N, false) : sweep_smem<8>(N, false)) + 1024));
     int r = by_threads < by_smem ? by_threads : by_smem;
     if (N > 256 && r > 2) r = 2;  // ~128 registers per thread with several apexes per thread
+    if (N > 1024) r = 1;          // the tables of two resident clouds per SM (2 x 148 x 76 MB) thrash L2
     if (nth == 64 && r > 12) r = 12;  // measured: 129-256 points run best with 12 two-warp CTAs per SM
     return r < 1 ? 1 : r;
 }
@@ -987,8 +1088,8 @@ static bool make_plan(int B, int N, size_t ws_bytes, Plan& pl) {
     pl.ldT = (N + 31) & ~31;
     pl.Emax = c2(N);
     pl.ib = bits_for(pl.Emax);
-    pl.nth = N <= 128 ? 32 : (N <= 256 ? 64 : 256);
-    pl.apt = N <= 256 ? 4 : (N <= 512 ? 2 : (N <= 1024 ? 4 : 8));
+    pl.nth = N <= 128 ? 32 : (N <= 256 ? 64 : (N <= 512 ? 256 : 512));
+    pl.apt = N <= 256 ? 4 : (N <= 1024 ? 2 : 4);
     pl.tbytes = N <= 256 ? 2 : 4;
     long long cp = 64ll * N;
     pl.capP = (int)(cp < kCapPMax ? cp : kCapPMax);
@@ -1004,6 +1105,8 @@ static bool make_plan(int B, int N, size_t ws_bytes, Plan& pl) {
         pl.grid1 = C < kSms * per_sm ? C : kSms * per_sm;
         pl.grid2 = C < kGrid2 ? C : kGrid2;
         pl.counters = o; o += 256;
+        pl.nbirth = o; o += al((size_t)C * 4);   // (zeroed together with the counters)
+        pl.order = o; o += al((size_t)C * 4);
         pl.m = o; o += al((size_t)C * 4);
         pl.nanflag = o; o += al((size_t)C * 4);
         pl.list = o; o += al((size_t)C * 4);
@@ -1024,9 +1127,9 @@ static bool make_plan(int B, int N, size_t ws_bytes, Plan& pl) {
     };
     long long C = B < cmax ? B : cmax;
     if (C < 1) C = 1;
-    // sizing query (ws_bytes == 0): aim at <= 48 GB of the 180 GB (big clouds are latency-bound per CTA: the
+    // sizing query (ws_bytes == 0): aim at <= 64 GB of the 180 GB (big clouds are latency-bound per CTA: the
     // more of them are resident at once, two per SM, the better), at least one cloud
-    const size_t budget = ws_bytes ? ws_bytes : ((size_t)48 << 30);
+    const size_t budget = ws_bytes ? ws_bytes : ((size_t)64 << 30);
     layout((int)C);
     while (pl.total > budget && C > 1) { C = (C + 1) / 2; layout((int)C); }
     return ws_bytes == 0 || pl.total <= ws_bytes;
@@ -1044,6 +1147,7 @@ static cudaError_t launch_sweeps(Params p, const Plan& pl, char* w8, cudaStream_
         ProfScope prof("rips_large_sweep_t0", st);
         p.worklist = nullptr; p.n_work = nullptr;
         p.overflow_list = (int*)(w8 + pl.list0); p.n_overflow = counters + 1;
+        p.queue = counters + 8;
         const size_t smem = sweep_smem<WN>(p.N, false);
         e = cudaFuncSetAttribute(sweep_kernel<NTH, APT, WN, false, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -1057,6 +1161,7 @@ static cudaError_t launch_sweeps(Params p, const Plan& pl, char* w8, cudaStream_
         ProfScope prof("rips_large_sweep_t1", st);
         p.worklist = W0 > 0 ? (const int*)(w8 + pl.list0) : nullptr; p.n_work = W0 > 0 ? counters + 1 : nullptr;
         p.overflow_list = (int*)(w8 + pl.list); p.n_overflow = counters;
+        p.queue = counters + 9;
         const size_t smem = sweep_smem<W1>(p.N, false);
         e = cudaFuncSetAttribute(sweep_kernel<NTH, APT, W1, false, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -1071,7 +1176,8 @@ static cudaError_t launch_sweeps(Params p, const Plan& pl, char* w8, cudaStream_
         p.worklist = (const int*)(w8 + pl.list); p.n_work = counters;
         p.overflow_list = nullptr; p.n_overflow = nullptr;
         p.phic = (uint32_t*)(w8 + pl.phic2);
-        constexpr bool SG = (APT > 4);
+        p.queue = counters + 10;
+        constexpr bool SG = (NTH * APT > 1024);   // above 1,024 points S[v][32] does not fit shared memory
         const size_t smem = sweep_smem<32>(p.N, SG);
         e = cudaFuncSetAttribute(sweep_kernel<NTH, APT, 32, SG, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -1119,11 +1225,12 @@ extern "C" int tda_rips_h01_large(const float* D, const int* npts, int B, int N,
     p.phic = nullptr; p.pcr = (uint32_t*)(w8 + pl.pcr); p.act = (uint32_t*)(w8 + pl.act);
     p.rec = (uint32_t*)(w8 + pl.rec); p.sglob = (uint32_t*)(w8 + pl.sglob);
     p.worklist = nullptr; p.n_work = nullptr; p.overflow_list = nullptr; p.n_overflow = nullptr;
+    p.queue = nullptr; p.order = nullptr; p.nbirth = (int*)(w8 + pl.nbirth);
     cudaError_t e;
     for (int c0 = 0; c0 < B; c0 += pl.C) {
         const int C = (B - c0) < pl.C ? (B - c0) : pl.C;
         p.c0 = c0; p.C = C;
-        if ((e = cudaMemsetAsync(w8 + pl.counters, 0, 256, st)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemsetAsync(w8 + pl.counters, 0, pl.order - pl.counters, st)) != cudaSuccess) return (int)e;
         {
             // keys + per-CTA radix sort + rank matrix in one kernel (fills T, Q, m, nanflag of the chunk)
             ProfScope prof("rips_large_rank", st);
@@ -1154,13 +1261,22 @@ extern "C" int tda_rips_h01_large(const float* D, const int* npts, int B, int N,
             count_launch();
             if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
         }
-        // 256 threads whatever the size (block barriers are what a visited edge pays for), 1-8 apexes each
-        // (small clouds: one or two warps per cloud, the visited edges are issue-bound there)
+        p.order = nullptr;
+        if (C > 1 && C <= 8192) {   // heaviest clouds first (quadratic in the clouds of the chunk: 0.05 ms at 8,192)
+            order_kernel<<<(C + 255) / 256, 256, 0, st>>>(p, (int*)(w8 + pl.order));
+            count_launch();
+            if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+            p.order = (const int*)(w8 + pl.order);
+        }
+        // small clouds: one or two warps per cloud (the visited edges are issue-bound there); above 256 points 256
+        // threads, above 512 points 512 threads (measured against 256 and 1,024: a visited edge is a chain of
+        // global round trips and block barriers, more threads shorten the row scans, more warps lengthen the
+        // barriers), 2-4 apexes per thread
         if (N <= 128) e = launch_sweeps<32, 4, 2, 8, uint16_t>(p, pl, w8, st);
         else if (N <= 256) e = launch_sweeps<64, 4, 2, 8, uint16_t>(p, pl, w8, st);
         else if (N <= 512) e = launch_sweeps<256, 2, 0, 8, uint32_t>(p, pl, w8, st);
-        else if (N <= 1024) e = launch_sweeps<256, 4, 0, 8, uint32_t>(p, pl, w8, st);
-        else e = launch_sweeps<256, 8, 0, 16, uint32_t>(p, pl, w8, st);
+        else if (N <= 1024) e = launch_sweeps<512, 2, 0, 8, uint32_t>(p, pl, w8, st);
+        else e = launch_sweeps<512, 4, 0, 16, uint32_t>(p, pl, w8, st);
         if (e != cudaSuccess) return (int)e;
     }
     return 0;

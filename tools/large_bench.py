@@ -38,8 +38,9 @@ def timed(fn, n=3, warm=1):
     return e0.elapsed_time(e1) / n
 
 
-CASES = [("large", 64, 1000, 2.0), ("large", 64, 1500, 2.0), ("large", 64, 2000, 2.0), ("large", 64, 2000, 0.25),
-         ("large", 296, 1000, 2.0), ("large", 148, 2000, 2.0), ("large", 296, 2000, 2.0), ("large", 444, 2000, 2.0),
+CASES = [("large", 64, 1000, 2.0), ("large", 64, 2000, 2.0), ("large", 64, 2000, 0.25),
+         ("large", 296, 1000, 2.0), ("large", 592, 1000, 2.0), ("large", 1184, 1000, 2.0),
+         ("large", 148, 2000, 2.0), ("large", 296, 2000, 2.0), ("large", 592, 2000, 2.0),
          ("large", 8192, 124, 2.0), ("large", 8192, 248, 2.0)]
 
 
