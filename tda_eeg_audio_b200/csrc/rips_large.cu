@@ -49,6 +49,7 @@ namespace tda {
 namespace rips_large {
 
 constexpr int kMaxN = 2048;
+constexpr int kSmCount = 148;   // B200
 constexpr uint32_t kInf = 0xFFFFFFFFu;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 constexpr uint32_t kEssential = 0xFFFFFFFFu;
@@ -310,6 +311,200 @@ __global__ void __launch_bounds__(kRankThreads, 1) rank_kernel(Params p) {
     }
 }
 
+// K1 for clouds up to 256 points (the audio path: Takens clouds of 97-248 points): the (key, (i, j)) array
+// of a cloud -- at most 32,640 elements of 32 + 16 bits -- stays in shared memory for the whole sort.  A pass is
+// in place: every warp owns a contiguous segment, its lanes hold the segment's elements in registers, and once
+// everybody has read (barrier) the elements are scattered to their stable positions (digit base + the counts of
+// the earlier warps + the earlier chunks of the own warp + the lower lanes with the same digit); the 16-bit
+// payloads follow in a second round through the saved positions, so that never more than EPT + EPT / 2 data
+// registers are live.  Nothing but D is read from and nothing but P, the sorted keys, T and Q is written to
+// global memory; T is assembled in the key array's space and leaves as 16-byte rows.
+constexpr int kCntStride = 258;   // u16 per counter row: 516 bytes, rows start in different banks
+template <int NTH, int EPT> struct RankSmall {
+    static constexpr int NW = NTH / 32;
+    static constexpr int kCap = NTH * EPT;
+    static constexpr size_t kKeyBytes = (size_t)kCap * 4;
+    static constexpr size_t kSmem = kKeyBytes + (size_t)kCap * 2 + (size_t)NW * kCntStride * 2 + 256 * 4 + 256 * 4 + 4 * NW * 4 + 64;
+};
+
+template <int NTH, int EPT, int MINB>
+__global__ void __launch_bounds__(NTH, MINB) rank_small_kernel(Params p) {
+    using RS = RankSmall<NTH, EPT>;
+    constexpr int NW = RS::NW;
+    constexpr int DPW = 256 / NW;   // digits scanned per warp
+    extern __shared__ __align__(16) unsigned char rs_raw[];
+    uint32_t* K = reinterpret_cast<uint32_t*>(rs_raw);                                  // [kCap] keys; later T
+    uint16_t* Pp = reinterpret_cast<uint16_t*>(rs_raw + RS::kKeyBytes);                 // [kCap] i << 8 | j
+    uint16_t* cnt = Pp + RS::kCap;                                                      // [NW][kCntStride]
+    uint32_t* tot = reinterpret_cast<uint32_t*>(cnt + NW * kCntStride);                 // [256] elements per digit
+    uint32_t* dbase = tot + 256;                                                        // [256] first position per digit
+    uint32_t* red = dbase + 256;                                                        // [4 NW]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int c = blockIdx.x; c < p.C; c += gridDim.x) {
+        const int b = p.c0 + c;
+        const int n = cloud_n(p, b);
+        const int E = (int)c2(n);
+        const float* Db = p.D + (size_t)b * p.strideB;
+        // ---- keys in descending edge index (a warp per matrix row, lanes along the row: coalesced reads)
+        int valid = 0, nan_seen = 0;
+        uint32_t k_or = 0, k_and = 0xFFFFFFFFu;
+        for (int j = warp; j < n - 1; j += NW) {
+            const float* row = Db + (size_t)j * p.ld;
+            for (int i = j + 1 + lane; i < n; i += 32) {
+                const float d = __ldg(row + i) + 0.0f;
+                nan_seen |= (d != d);
+                const bool ok = d <= p.thresh;
+                const uint32_t key = ok ? float_key(d) : kInf;
+                const int pos = E - 1 - (i * (i - 1) / 2 + j);
+                K[pos] = key;
+                Pp[pos] = (uint16_t)((i << 8) | j);
+                if (ok) { ++valid; k_or |= key; k_and &= key; }
+            }
+        }
+        valid = __reduce_add_sync(kFull, valid);
+        nan_seen = __reduce_or_sync(kFull, nan_seen);
+        k_or = __reduce_or_sync(kFull, k_or);
+        k_and = __reduce_and_sync(kFull, k_and);
+        if (lane == 0) { red[warp] = (uint32_t)valid; red[NW + warp] = k_or; red[2 * NW + warp] = k_and; red[3 * NW + warp] = (uint32_t)nan_seen; }
+        __syncthreads();
+        int m = 0;
+        uint32_t vor = 0, vand = 0xFFFFFFFFu, any_nan = 0;
+        for (int w = 0; w < NW; ++w) { m += (int)red[w]; vor |= red[NW + w]; vand &= red[2 * NW + w]; any_nan |= red[3 * NW + w]; }
+        // with absent edges (d > thresh, NaN) in between every pass runs: they have to travel to the end
+        const uint32_t varying = (m < E) ? 0xFFFFFFFFu : (vor ^ vand);
+        const int nch = (E + NTH - 1) / NTH;          // chunks of 32 elements per warp
+        const int seg0 = warp * nch * 32;             // first element of this warp's segment
+        uint32_t* row32 = reinterpret_cast<uint32_t*>(cnt + warp * kCntStride);
+        for (int pass = 0; pass < 4; ++pass) {
+            const int sh = 8 * pass;
+            if (!((varying >> sh) & 255u)) continue;
+            {
+                uint32_t* c32 = reinterpret_cast<uint32_t*>(cnt);
+                for (int q = tid; q < NW * kCntStride / 2; q += NTH) c32[q] = 0;
+            }
+            __syncthreads();
+            // ---- this warp's segment into registers, its digits counted into the warp's counter row
+            uint32_t kr[EPT];
+#pragma unroll
+            for (int t = 0; t < EPT; ++t) {
+                const int k = seg0 + 32 * t + lane;
+                const bool act = t < nch && k < E;
+                kr[t] = act ? K[k] : 0u;
+                if (act) {
+                    const uint32_t dg = (kr[t] >> sh) & 255u;
+                    atomicAdd(row32 + (dg >> 1), 1u << (16 * (dg & 1u)));
+                }
+            }
+            __syncthreads();
+            // ---- per digit: exclusive scan over the warps (lane = warp row), total per digit
+#pragma unroll
+            for (int dd = 0; dd < DPW; ++dd) {
+                const int d = warp * DPW + dd;
+                const uint32_t own = lane < NW ? cnt[lane * kCntStride + d] : 0u;
+                uint32_t incl = own;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(kFull, incl, o);
+                    if (lane >= o) incl += y;
+                }
+                if (lane < NW) cnt[lane * kCntStride + d] = (uint16_t)(incl - own);
+                if (lane == 31) tot[d] = incl;
+            }
+            __syncthreads();
+            if (warp == 0) {   // first position of every digit: eight digits per lane
+                uint32_t v[8], run = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { v[q] = tot[8 * lane + q]; run += v[q]; }
+                uint32_t incl = run;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(kFull, incl, o);
+                    if (lane >= o) incl += y;
+                }
+                uint32_t base = incl - run;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { dbase[8 * lane + q] = base; base += v[q]; }
+            }
+            __syncthreads();
+            // ---- keys to their positions (stable: chunks in order, lanes ranked inside a chunk)
+            uint32_t ps[EPT / 2];
+#pragma unroll
+            for (int t = 0; t < EPT; ++t) {
+                const int k = seg0 + 32 * t + lane;
+                const bool act = t < nch && k < E;
+                const uint32_t dg = act ? ((kr[t] >> sh) & 255u) : (256u + lane);   // idle lanes: no peers
+                const uint32_t peers = __match_any_sync(kFull, dg);
+                // the first lane of a digit group takes the group's slots from the warp's counter (one atomic on the
+                // packed pair of 16-bit counters: no carry, a cloud has fewer than 2^16 edges) and hands the old value
+                // on -- no read / barrier / write chain from one chunk to the next
+                const int leader = __ffs(peers) - 1;
+                uint32_t old = 0;
+                if (act && lane == leader) old = atomicAdd(row32 + (dg >> 1), (uint32_t)__popc(peers) << (16 * (dg & 1u)));
+                old = __shfl_sync(kFull, old, leader);
+                uint32_t pos = 0;
+                if (act) {
+                    pos = dbase[dg] + ((old >> (16 * (dg & 1u))) & 0xFFFFu) + __popc(peers & lt);
+                    K[pos] = kr[t];
+                }
+                if (t & 1) ps[t >> 1] |= pos << 16; else ps[t >> 1] = pos;
+            }
+            // ---- the payloads follow through the saved positions
+            uint32_t pv[EPT / 2];
+#pragma unroll
+            for (int t = 0; t < EPT; ++t) {
+                const int k = seg0 + 32 * t + lane;
+                const bool act = t < nch && k < E;
+                const uint32_t v = act ? (uint32_t)Pp[k] : 0u;
+                if (t & 1) pv[t >> 1] |= v << 16; else pv[t >> 1] = v;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int t = 0; t < EPT; ++t) {
+                const int k = seg0 + 32 * t + lane;
+                const bool act = t < nch && k < E;
+                if (act) Pp[(ps[t >> 1] >> (16 * (t & 1))) & 0xFFFFu] = (uint16_t)((pv[t >> 1] >> (16 * (t & 1))) & 0xFFFFu);
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+        // ---- sorted position -> P and the sorted keys
+        uint32_t* Pc = p.P + (size_t)c * p.Emax;
+        uint32_t* sk = p.skey + (size_t)c * p.Emax;
+        for (int r = tid; r < m; r += NTH) {
+            const uint32_t key = K[r], pay = Pp[r];
+            const bool tie = r + 1 < m && K[r + 1] == key;
+            Pc[r] = (pay & 255u) | ((pay >> 8) << 11) | (tie ? kTieNext : 0u);
+            sk[r] = key;
+        }
+        __syncthreads();
+        // ---- the rank matrix, assembled in the key array's space, leaves as 16-byte rows; Q = none
+        uint16_t* Ts = reinterpret_cast<uint16_t*>(K);
+        const int ldT = p.ldT;
+        const int nt4 = n * ldT * 2 / 16;
+        {
+            uint4* t4 = reinterpret_cast<uint4*>(Ts);
+            for (int q = tid; q < nt4; q += NTH) t4[q] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        }
+        __syncthreads();
+        for (int r = tid; r < m; r += NTH) {
+            const uint32_t pay = Pp[r];
+            const int i = (int)(pay >> 8), j = (int)(pay & 255u);
+            Ts[i * ldT + j] = (uint16_t)r;
+            Ts[j * ldT + i] = (uint16_t)r;
+        }
+        __syncthreads();
+        {
+            uint4* tg = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.T) + (size_t)c * p.N * ldT);
+            uint4* qg = reinterpret_cast<uint4*>(p.Q + (size_t)c * p.N * ldT);
+            const uint4* t4 = reinterpret_cast<const uint4*>(Ts);
+            for (int q = tid; q < nt4; q += NTH) { tg[q] = t4[q]; qg[q] = make_uint4(0u, 0u, 0u, 0u); }
+        }
+        if (tid == 0) { p.m[c] = n >= 2 ? m : 0; p.nanflag[c] = any_nan ? 1 : 0; }
+        __syncthreads();   // the arrays are rewritten for the next cloud
+    }
+}
+
 // block-wide minimum of an int (every thread gets the result); sm[] holds >= 33 ints
 template <int NTH> __device__ __forceinline__ int block_min(int v, int* sm) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -417,7 +612,9 @@ template <int NTH> __global__ void __launch_bounds__(NTH) kruskal_kernel(Params 
 // Lanes of a warp hold consecutive ranks, i.e. edges of nearly equal length whose neighbourhoods
 // are equally dense, so their scans have similar lengths (~2 sqrt(N) on average: most edges are
 // late and find an apex within the first few candidates).
-template <typename TT>
+// ONLY_TIED: the members of tie runs only (the audio path classifies everything else from adjacency bit rows,
+// classify_bits_kernel below)
+template <typename TT, bool ONLY_TIED>
 __global__ void __launch_bounds__(256) classify_kernel(Params p) {
     constexpr int VPL = 16 / (int)sizeof(TT);   // ranks per 16-byte load
     constexpr uint32_t kAbsent = RankOf<TT>::kAbsent;
@@ -434,6 +631,7 @@ __global__ void __launch_bounds__(256) classify_kernel(Params p) {
         const uint32_t* keys = p.skey + (size_t)c * p.Emax;
         const int i = p_i(q), j = p_j(q);
         const bool tied = (q & kTieNext) || (r > 0 && (Pc[r - 1] & kTieNext));
+        if (ONLY_TIED && !tied) continue;
         const uint32_t k32r = tied ? keys[r] : 0u;
         const uint4* Ti = reinterpret_cast<const uint4*>(Tc + (size_t)i * p.ldT);
         const uint4* Tj = reinterpret_cast<const uint4*>(Tc + (size_t)j * p.ldT);
@@ -462,6 +660,90 @@ __global__ void __launch_bounds__(256) classify_kernel(Params p) {
         }
         if (dv < 0) { Pc[r] = q | kBirth; atomicAdd(p.nbirth + c, 1); }
         else p.defv[(size_t)c * p.Emax + r] = (uint16_t)dv;
+    }
+}
+
+// K4 for clouds up to 256 points (the audio path): one WARP per cloud walks the sorted edge list 32 ranks at a
+// time and keeps the adjacency of all earlier ranks as bit rows in shared memory, so "the largest apex whose two
+// other edges are earlier" is the top bit of adj[i] & adj[j] -- all apexes of an edge in a handful of word
+// operations, 32 edges per step -- instead of a walk down two rank rows per edge (which cost as much as the sort).
+// Edges of the same step that share a vertex with the lane's edge are looked at one by one (touched[v] = lanes
+// of the step with an edge at v); members of tie runs are left to classify_kernel<ONLY_TIED>.
+template <int NWORDS>   // 32-bit words per adjacency row: 4 up to 128 points, 8 up to 256
+__global__ void __launch_bounds__(256) classify_bits_kernel(Params p) {
+    extern __shared__ __align__(16) uint32_t cb_raw[];
+    constexpr int NV = 32 * NWORDS;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    uint32_t* adj = cb_raw + (size_t)wib * (NV * NWORDS + NV);   // [NV][NWORDS]
+    uint32_t* touched = adj + NV * NWORDS;                         // [NV]
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int c = blockIdx.x * wpb + wib; c < p.C; c += gridDim.x * wpb) {
+        const int n = cloud_n(p, p.c0 + c);
+        const int m = n >= 2 ? p.m[c] : 0;
+        uint32_t* Pc = p.P + (size_t)c * p.Emax;
+        uint16_t* dvc = p.defv + (size_t)c * p.Emax;
+        for (int q = lane; q < NV * NWORDS + NV; q += 32) adj[q] = 0;
+        __syncwarp();
+        int births = 0;
+        uint32_t prev_tie = 0;   // "rank c0 - 1 has the same length as rank c0"
+        uint32_t qn = lane < m ? __ldg(Pc + lane) : 0u;
+        for (int c0 = 0; c0 < m; c0 += 32) {
+            const int r = c0 + lane;
+            const bool act = r < m;
+            const uint32_t q = qn;
+            qn = r + 32 < m ? __ldg(Pc + r + 32) : 0u;   // (the flags this kernel sets are not read back)
+            const int i = p_i(q), j = p_j(q);
+            const uint32_t tn = __ballot_sync(kFull, act && (q & kTieNext));
+            const bool tied = ((tn >> lane) & 1u) || (lane ? ((tn >> (lane - 1)) & 1u) : prev_tie);
+            prev_tie = tn >> 31;
+            if (act) { atomicOr(touched + i, 1u << lane); atomicOr(touched + j, 1u << lane); }
+            __syncwarp();
+            const bool want = act && !(q & kMst) && !tied;
+            int vc = -1;
+            uint32_t tl = 0;
+            if (want) {
+                const uint4* ai = reinterpret_cast<const uint4*>(adj + i * NWORDS);
+                const uint4* aj = reinterpret_cast<const uint4*>(adj + j * NWORDS);
+#pragma unroll
+                for (int w4 = NWORDS / 4 - 1; w4 >= 0; --w4) {
+                    const uint4 a = ai[w4], b = aj[w4];
+                    const uint32_t cm[4] = {a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w};
+#pragma unroll
+                    for (int k = 3; k >= 0; --k)
+                        if (vc < 0 && cm[k]) vc = 32 * (4 * w4 + k) + 31 - __clz(cm[k]);
+                }
+                tl = (touched[i] | touched[j]) & lt;
+            }
+            while (__any_sync(kFull, tl != 0)) {
+                const int l2 = tl ? __ffs(tl) - 1 : lane;
+                const uint32_t q2 = __shfl_sync(kFull, q, l2);
+                if (tl) {
+                    tl &= tl - 1;
+                    const int a = p_i(q2), b = p_j(q2);
+                    const bool at_a = (a == i) || (a == j);
+                    const int s = at_a ? a : b, v = at_a ? b : a;   // shared vertex, candidate apex
+                    const int o = (s == i) ? j : i;                 // the end point of this edge that is not shared
+                    if (v > vc) {
+                        bool ok = (adj[o * NWORDS + (v >> 5)] >> (v & 31)) & 1u;
+                        if (!ok) ok = (touched[o] & touched[v] & lt) != 0;   // edge (o, v) earlier in this step
+                        if (ok) vc = v;
+                    }
+                }
+            }
+            __syncwarp();
+            if (act) { touched[i] = 0; touched[j] = 0; }
+            if (want) {
+                if (vc < 0) { Pc[r] = q | kBirth; ++births; }
+                else dvc[r] = (uint16_t)vc;
+            }
+            if (act) {
+                atomicOr(adj + i * NWORDS + (j >> 5), 1u << (j & 31));
+                atomicOr(adj + j * NWORDS + (i >> 5), 1u << (i & 31));
+            }
+            __syncwarp();
+        }
+        births = __reduce_add_sync(kFull, births);
+        if (lane == 0 && births) atomicAdd(p.nbirth + c, births);
     }
 }
 
@@ -1053,6 +1335,15 @@ __global__ void __launch_bounds__(NTH) sweep_kernel(Params p, int rezero_q) {
     }
 }
 
+template <int NTH, int EPT, int MINB> static cudaError_t launch_rank_small(const Params& p, cudaStream_t st) {
+    const size_t smem = RankSmall<NTH, EPT>::kSmem;
+    cudaError_t e = cudaFuncSetAttribute(rank_small_kernel<NTH, EPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int grid = p.C < kSmCount * MINB ? p.C : kSmCount * MINB;
+    rank_small_kernel<NTH, EPT, MINB><<<grid, NTH, smem, st>>>(p);
+    return cudaSuccess;
+}
+
 template <int W> static size_t sweep_smem(int N, bool sg) {
     size_t words = kMaxN / 32 + W + W + 32 * W + 32 * W + W + W + 4 + 34 + 8;
     if (!sg) words += (size_t)N * W;
@@ -1235,13 +1526,15 @@ extern "C" int tda_rips_h01_large(const float* D, const int* npts, int B, int N,
             // keys + per-CTA radix sort + rank matrix in one kernel (fills T, Q, m, nanflag of the chunk)
             ProfScope prof("rips_large_rank", st);
             const int grid = C < kSms ? C : kSms;
-            if (N <= 256) {
-                cudaFuncSetAttribute(rank_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRankSmem);
-                rank_kernel<uint16_t><<<grid, kRankThreads, kRankSmem, st>>>(p);
-            } else {
+            if (N <= 128) e = launch_rank_small<512, 16, 3>(p, st);          // E <= 8,128: three clouds per SM
+            else if (N <= 170) e = launch_rank_small<512, 32, 2>(p, st);     // E <= 14,365, T <= 64 KB: two
+            else if (N <= 256) e = launch_rank_small<1024, 32, 1>(p, st);    // E <= 32,640: 209 KB, one
+            else {
                 cudaFuncSetAttribute(rank_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRankSmem);
                 rank_kernel<uint32_t><<<grid, kRankThreads, kRankSmem, st>>>(p);
+                e = cudaSuccess;
             }
+            if (e != cudaSuccess) return (int)e;
             count_launch();
             if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
         }
@@ -1256,9 +1549,25 @@ extern "C" int tda_rips_h01_large(const float* D, const int* npts, int B, int N,
             ProfScope prof("rips_large_classify", st);
             long long blocks = (pl.Emax * C + 255) / 256;
             if (blocks > 148 * 64) blocks = 148 * 64;
-            if (N <= 256) classify_kernel<uint16_t><<<(unsigned)blocks, 256, 0, st>>>(p);
-            else classify_kernel<uint32_t><<<(unsigned)blocks, 256, 0, st>>>(p);
-            count_launch();
+            if (N > 256) {
+                classify_kernel<uint32_t, false><<<(unsigned)blocks, 256, 0, st>>>(p);
+                count_launch();
+            } else {
+                const int nwords = N <= 128 ? 4 : 8;
+                const size_t smem = (size_t)8 * (32 * nwords * nwords + 32 * nwords) * 4;
+                int g = (C + 7) / 8;
+                const int gmax = kSms * (N <= 128 ? 8 : 3);
+                if (g > gmax) g = gmax;
+                if (N <= 128) classify_bits_kernel<4><<<g, 256, smem, st>>>(p);
+                else {
+                    cudaFuncSetAttribute(classify_bits_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    classify_bits_kernel<8><<<g, 256, smem, st>>>(p);
+                }
+                count_launch();
+                if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+                classify_kernel<uint16_t, true><<<(unsigned)blocks, 256, 0, st>>>(p);   // members of tie runs
+                count_launch();
+            }
             if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
         }
         p.order = nullptr;

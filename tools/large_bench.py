@@ -46,8 +46,9 @@ CASES = [("large", 64, 1000, 2.0), ("large", 64, 2000, 2.0), ("large", 64, 2000,
 
 def main():
     cases = CASES
-    if len(sys.argv) > 1:
-        cases = [c for c in cases if c[0] in sys.argv[1:]]
+    if len(sys.argv) > 1:   # point counts to run, e.g. `large_bench.py 124 248`
+        want = {int(a) for a in sys.argv[1:]}
+        cases = [c for c in cases if c[2] in want]
     for engine, B, n, thr in cases:
         D = takens_clouds(B, n)
         out = {}
