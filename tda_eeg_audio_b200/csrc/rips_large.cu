@@ -618,10 +618,10 @@ template <typename TT, bool ONLY_TIED>
 __global__ void __launch_bounds__(256) classify_kernel(Params p) {
     constexpr int VPL = 16 / (int)sizeof(TT);   // ranks per 16-byte load
     constexpr uint32_t kAbsent = RankOf<TT>::kAbsent;
-    const long long total = p.Emax * p.C;
-    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(w / p.Emax);
-        const int r = (int)(w - (long long)c * p.Emax);
+    const uint32_t total = (uint32_t)(p.Emax * p.C), emax = (uint32_t)p.Emax;   // (< 2^31: make_plan)
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
+        const int c = (int)(w / emax);
+        const int r = (int)(w - (uint32_t)c * emax);
         if (r >= p.m[c]) continue;
         uint32_t* Pc = p.P + (size_t)c * p.Emax;
         const uint32_t q = Pc[r];
@@ -789,6 +789,10 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
     const float* Db;
     int n, m, ldT, ld, tid, lane, warp, capP, capR;
 
+    // a one-warp CTA needs no block barrier
+    __device__ __forceinline__ void bar() const {
+        if constexpr (NTH == 32) __syncwarp(); else __syncthreads();
+    }
     __device__ __forceinline__ float dist(int a, int b) const {
         return Db[(size_t)min(a, b) * ld + max(a, b)] + 0.0f;
     }
@@ -884,9 +888,9 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
         const int npc = ctl[0];
         for (int q = tid; q < npc * W; q += NTH) phic[q] &= live[q % W];
         for (int q = tid; q < n * W; q += NTH) S[q] &= live[q % W];
-        __syncthreads();
+        bar();
         if (tid < W) used[tid] = live[tid];
-        __syncthreads();
+        bar();
     }
     // o ^= compact entry idx (a mask of W words = 8 W bytes, aligned: 16-byte loads)
     __device__ __forceinline__ void xor_entry(int idx, uint32_t (&o)[W]) const {
@@ -989,7 +993,7 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
                 for (int w = 0; w < W; ++w) cv[w] = c[w];
                 ctl[5] = best_pr;
             }
-            __syncthreads();
+            bar();
             // youngest class of the mask dies
             int slot = -1, age = -1;
             bool others = false;
@@ -1005,7 +1009,7 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
             }
             const int sw = slot >> 5;
             const uint32_t sb = 1u << (slot & 31);
-            __syncthreads();
+            bar();
             if (tid == 0) {
                 if (age < r0) {  // non-zero persistence
                     const int k = ctl[2];
@@ -1056,9 +1060,9 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
                     }
                 }
             }
-            __syncthreads();
+            bar();
             rebuild_hot();
-            __syncthreads();
+            bar();
             if (ctl[3]) return;
         }
     }
@@ -1066,20 +1070,20 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
     // a tie run [r0, r1): A (births / definitions in rank order, warp 0, scrubs when slots run out), B
     __device__ void generic_run(int r0, int r1) {
         if (tid == 0) ctl[1] = 0;
-        __syncthreads();
+        bar();
         int ra = r0;
         while (true) {
             if (warp == 0) {
                 const int nxt = step_a(ra, r1);
                 if (lane == 0) ctl[4] = nxt;
             }
-            __syncthreads();
+            bar();
             ra = ctl[4];
             if (ra >= r1 || ctl[3]) break;
             scrub();  // slots exhausted at rank ra: recycle the dead ones
             bool room = false;
             for (int w = 0; w < W; ++w) room |= (~used[w]) != 0;
-            if (!room) { if (tid == 0) ctl[3] = 1; __syncthreads(); break; }
+            if (!room) { if (tid == 0) ctl[3] = 1; bar(); break; }
         }
         if (ctl[3]) return;
         if (ctl[1] > 0) step_b(r0, r1);
@@ -1097,19 +1101,31 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
         // apex of (thread, h): four CONSECUTIVE apexes per thread when the ranks are 16-bit (clouds up to
         // 256 points: NTH * 4 covers the padded row), so each of the four rows is one 8-byte load per thread;
         // the padding of a row is "absent" in T and 0 in Q (rank_kernel), no bounds test needed
-        constexpr bool kVec = sizeof(TT) == 2 && APT == 4;
+        constexpr bool kVec = sizeof(TT) == 2 && (APT == 4 || APT == 8);
         if constexpr (kVec) {
-            uint2 a = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu), b = a, qx = make_uint2(0u, 0u), qy = qx;
-            if (4 * tid < ldT) {
-                a = __ldg(reinterpret_cast<const uint2*>(Tx) + tid);
-                b = __ldg(reinterpret_cast<const uint2*>(Ty) + tid);
-                qx = reinterpret_cast<const uint2*>(Qx)[tid];
-                qy = reinterpret_cast<const uint2*>(Qy)[tid];
+            // APT consecutive apexes per thread: each of the four rows is one 8- or 16-byte load per thread
+            uint32_t a[APT / 2], b[APT / 2], qx[APT / 2], qy[APT / 2];
+#pragma unroll
+            for (int k = 0; k < APT / 2; ++k) { a[k] = 0xFFFFFFFFu; b[k] = 0xFFFFFFFFu; qx[k] = 0u; qy[k] = 0u; }
+            if (APT * tid < ldT) {
+                if constexpr (APT == 4) {
+                    const uint2 ta2 = __ldg(reinterpret_cast<const uint2*>(Tx) + tid), tb2 = __ldg(reinterpret_cast<const uint2*>(Ty) + tid);
+                    const uint2 qx2 = reinterpret_cast<const uint2*>(Qx)[tid], qy2 = reinterpret_cast<const uint2*>(Qy)[tid];
+                    a[0] = ta2.x; a[1] = ta2.y; b[0] = tb2.x; b[1] = tb2.y;
+                    qx[0] = qx2.x; qx[1] = qx2.y; qy[0] = qy2.x; qy[1] = qy2.y;
+                } else {
+                    const uint4 ta4 = __ldg(reinterpret_cast<const uint4*>(Tx) + tid), tb4 = __ldg(reinterpret_cast<const uint4*>(Ty) + tid);
+                    const uint4 qx4 = reinterpret_cast<const uint4*>(Qx)[tid], qy4 = reinterpret_cast<const uint4*>(Qy)[tid];
+                    a[0] = ta4.x; a[1] = ta4.y; a[2] = ta4.z; a[3] = ta4.w; b[0] = tb4.x; b[1] = tb4.y; b[2] = tb4.z; b[3] = tb4.w;
+                    qx[0] = qx4.x; qx[1] = qx4.y; qx[2] = qx4.z; qx[3] = qx4.w; qy[0] = qy4.x; qy[1] = qy4.y; qy[2] = qy4.z; qy[3] = qy4.w;
+                }
             }
-            ta[0] = a.x & 0xFFFFu; ta[1] = a.x >> 16; ta[2] = a.y & 0xFFFFu; ta[3] = a.y >> 16;
-            tb[0] = b.x & 0xFFFFu; tb[1] = b.x >> 16; tb[2] = b.y & 0xFFFFu; tb[3] = b.y >> 16;
-            qa[0] = qx.x & 0xFFFFu; qa[1] = qx.x >> 16; qa[2] = qx.y & 0xFFFFu; qa[3] = qx.y >> 16;
-            qb[0] = qy.x & 0xFFFFu; qb[1] = qy.x >> 16; qb[2] = qy.y & 0xFFFFu; qb[3] = qy.y >> 16;
+#pragma unroll
+            for (int h = 0; h < APT; ++h) {
+                const int sh = 16 * (h & 1);
+                ta[h] = (a[h >> 1] >> sh) & 0xFFFFu; tb[h] = (b[h >> 1] >> sh) & 0xFFFFu;
+                qa[h] = (int)((qx[h >> 1] >> sh) & 0xFFFFu); qb[h] = (int)((qy[h >> 1] >> sh) & 0xFFFFu);
+            }
         } else {
 #pragma unroll
             for (int h = 0; h < APT; ++h) {
@@ -1124,7 +1140,7 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
             const int code = edge_a(pr, pe, dv);
             if (lane == 0) ctl[6] = code;
         }
-        __syncthreads();
+        bar();
         const int code = ctl[6];
         if (code == 0 || ctl[3]) return;
         if (code == 2) { generic_run(pr, pr + 1); return; }
@@ -1179,7 +1195,7 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
         for (int q = tid; q < kMaxN / 32; q += NTH) hot[q] = 0;
         if (tid < W) { live[tid] = 0; used[tid] = 0; }
         if (tid < 8) ctl[tid] = 0;
-        __syncthreads();
+        bar();
         int rbase = 0;
         uint32_t pe = kMst, pe_nx = kMst;
         int dv = 0, dv_nx = 0;
@@ -1201,23 +1217,33 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
                                   ((pe & kBirth) || hotbit(p_i(pe)) || hotbit(p_j(pe)));
                 const int first = block_min<NTH>(flag ? rr : 0x7FFFFFFF, (int*)red);
                 if (first == 0x7FFFFFFF) break;
-                if (rr == first) { pub[0] = pe; pub[2] = (uint32_t)dv; }
-                if (rr == first - 1) pub[1] = pe;
-                __syncthreads();
-                const uint32_t fpe = pub[0];
-                uint32_t ppe = 0;
-                if (first > rbase) ppe = pub[1];
-                else if (first > 0) ppe = __ldg(P + first - 1);
+                uint32_t fpe, ppe = 0;
+                int fdv;
+                if constexpr (NTH == 32) {   // the chunk is the warp's registers: shuffles, no shared memory, no barrier
+                    fpe = __shfl_sync(kFull, pe, first - rbase);
+                    fdv = __shfl_sync(kFull, dv, first - rbase);
+                    const uint32_t pv = __shfl_sync(kFull, pe, (first - rbase + 31) & 31);
+                    if (first > rbase) ppe = pv;
+                    else if (first > 0) ppe = __ldg(P + first - 1);
+                } else {
+                    if (rr == first) { pub[0] = pe; pub[2] = (uint32_t)dv; }
+                    if (rr == first - 1) pub[1] = pe;
+                    bar();
+                    fpe = pub[0];
+                    fdv = (int)pub[2];
+                    if (first > rbase) ppe = pub[1];
+                    else if (first > 0) ppe = __ldg(P + first - 1);
+                }
                 int r1 = first + 1;
                 if (!((fpe | ppe) & kTieNext)) {
-                    fast_single(first, fpe, (int)pub[2]);
+                    fast_single(first, fpe, fdv);
                 } else {
                     int r0 = first;
                     while (r0 > 0 && (__ldg(P + r0 - 1) & kTieNext)) --r0;
                     while (__ldg(P + r1 - 1) & kTieNext) ++r1;
                     generic_run(r0, r1);
                 }
-                __syncthreads();
+                bar();
                 done = r1;
                 if (done >= rend || ctl[3]) break;
             }
@@ -1229,7 +1255,7 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
                 if (rbase + tid < m) { pe = __ldg(P + rbase + tid); dv = defv[rbase + tid]; }
             }
         }
-        __syncthreads();
+        bar();
         const bool overflow = ctl[3] != 0;
         if (overflow) {
             if (p.overflow_list) {
@@ -1238,7 +1264,7 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
                 p.status[b] = TDA_ST_INTERNAL | (p.nanflag[c] ? TDA_ST_NAN_INPUT : 0);
                 p.counts[2 * b + 1] = 0;
             }
-            __syncthreads();
+            bar();
             return;
         }
         // ---- classes still alive are essential
@@ -1259,14 +1285,14 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
             }
             ctl[2] = k;
         }
-        __syncthreads();
+        bar();
         const int n1 = ctl[2];
         if (n1 > capR) {
             if (tid == 0) {
                 p.status[b] = TDA_ST_INTERNAL | (p.nanflag[c] ? TDA_ST_NAN_INPUT : 0);
                 p.counts[2 * b + 1] = 0;
             }
-            __syncthreads();
+            bar();
             return;
         }
         // ---- H1 rows in ripser's order: descending birth rank
@@ -1292,7 +1318,7 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
             p.counts[2 * b + 1] = n1;
             p.status[b] = (p.nanflag[c] ? TDA_ST_NAN_INPUT : 0) | (n1 > p.cap1 ? TDA_ST_H1_TRUNCATED : 0);
         }
-        __syncthreads();
+        bar();
     }
 };
 
@@ -1379,8 +1405,8 @@ static bool make_plan(int B, int N, size_t ws_bytes, Plan& pl) {
     pl.ldT = (N + 31) & ~31;
     pl.Emax = c2(N);
     pl.ib = bits_for(pl.Emax);
-    pl.nth = N <= 128 ? 32 : (N <= 256 ? 64 : (N <= 512 ? 256 : 512));
-    pl.apt = N <= 256 ? 4 : (N <= 1024 ? 2 : 4);
+    pl.nth = N <= 256 ? 32 : (N <= 512 ? 256 : 512);
+    pl.apt = N <= 128 ? 4 : (N <= 256 ? 8 : (N <= 1024 ? 2 : 4));
     pl.tbytes = N <= 256 ? 2 : 4;
     long long cp = 64ll * N;
     pl.capP = (int)(cp < kCapPMax ? cp : kCapPMax);
@@ -1565,6 +1591,7 @@ extern "C" int tda_rips_h01_large(const float* D, const int* npts, int B, int N,
                 }
                 count_launch();
                 if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+                ProfScope prof2("rips_large_classify_tied", st);
                 classify_kernel<uint16_t, true><<<(unsigned)blocks, 256, 0, st>>>(p);   // members of tie runs
                 count_launch();
             }
@@ -1582,7 +1609,7 @@ extern "C" int tda_rips_h01_large(const float* D, const int* npts, int B, int N,
         // global round trips and block barriers, more threads shorten the row scans, more warps lengthen the
         // barriers), 2-4 apexes per thread
         if (N <= 128) e = launch_sweeps<32, 4, 2, 8, uint16_t>(p, pl, w8, st);
-        else if (N <= 256) e = launch_sweeps<64, 4, 2, 8, uint16_t>(p, pl, w8, st);
+        else if (N <= 256) e = launch_sweeps<32, 8, 2, 8, uint16_t>(p, pl, w8, st);
         else if (N <= 512) e = launch_sweeps<256, 2, 0, 8, uint32_t>(p, pl, w8, st);
         else if (N <= 1024) e = launch_sweeps<512, 2, 0, 8, uint32_t>(p, pl, w8, st);
         else e = launch_sweeps<512, 4, 0, 16, uint32_t>(p, pl, w8, st);

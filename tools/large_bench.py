@@ -41,7 +41,7 @@ def timed(fn, n=3, warm=1):
 CASES = [("large", 64, 1000, 2.0), ("large", 64, 2000, 2.0), ("large", 64, 2000, 0.25),
          ("large", 296, 1000, 2.0), ("large", 592, 1000, 2.0), ("large", 1184, 1000, 2.0),
          ("large", 148, 2000, 2.0), ("large", 296, 2000, 2.0), ("large", 592, 2000, 2.0),
-         ("large", 8192, 124, 2.0), ("large", 8192, 248, 2.0)]
+         ("large", 8192, 124, 2.0), ("large", 8192, 248, 2.0), ("large", 32768, 124, 2.0), ("large", 32768, 248, 2.0)]
 
 
 def main():
@@ -59,7 +59,7 @@ def main():
             _lib.profile_enable(True)
             rips_h01_batched(D, thr, cap1=cap1, want_pairs=True, out=out, engine=engine)
             torch.cuda.synchronize()
-            for k in ("rank", "kruskal", "classify", "sweep_t0", "sweep_t1", "sweep_t2"):
+            for k in ("rank", "kruskal", "classify", "classify_tied", "sweep_t0", "sweep_t1", "sweep_t2"):
                 parts[k] = round(_lib.profile_query("rips_large_" + k)[0], 3)
             _lib.profile_enable(False)
         c = out["counts"]
