@@ -206,7 +206,10 @@ def secondary_workloads(dev, x_raw):
                        ("stress_1000pt", 296, 1000), ("stress_2000pt", 148, 2000),
                        # bigger batches: the sweep of a cloud is serial and a few clouds of a batch take several
                        # times the mean, so the device-side queue has something to balance
-                       ("stress_1000pt_1184clouds", 1184, 1000), ("stress_2000pt_592clouds", 592, 2000)):
+                       ("stress_1000pt_1184clouds", 1184, 1000), ("stress_2000pt_592clouds", 592, 2000),
+                       # the audio path at the batch size of a real run (1,416 recordings x 300 windows arrive as
+                       # chunks of 32,768 clouds): a batch of 8,192 lasts as long as its heaviest cloud
+                       ("audio_takens_124pt_32768clouds", 32768, 124), ("audio_takens_248pt_32768clouds", 32768, 248)):
         D = takens_clouds(B, n, dev=dev)
         buf = {}
         ms = timed_ms(lambda: rips_h01_batched(D, THRESH, cap1=4 * n, want_pairs=False, out=buf, engine="large"))

@@ -25,6 +25,12 @@
 // dt, g_k = min(f[i-1][k] + ds_i, f[i-1][k-1] + c_ik) -- a prefix minimum, i.e. a warp scan.  The c_ij
 // are the very same Gram-trick values.  46 x 113 cells instead of O(M^2 N) augmentation steps:
 // 19,200 EEG-vs-audio H0 pairs in 13.1 ms before (profiles/r02_wasserstein_h0_ncu.json).
+//
+// Pairs whose cost block does not fit an SM's shared memory (two diagrams of a few hundred points each: the
+// H0 diagrams of two 248-point clouds, anything from the 1,000-2,000-point clouds) take the BIG variant of the
+// same kernel: costs are evaluated where they are needed (the same expression, so the result is bit-identical),
+// the "column used" flags live in shared memory instead of one register bit per column, and what remains in
+// shared memory is linear in the number of points (up to ~4,000 points per pair).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -47,15 +53,27 @@ template <typename TIn> struct Params {
     int rows_cap, cols_cap;  // min / max of the two caps (+1 for the placeholder point)
 };
 
-__host__ __device__ inline size_t smem_bytes(int rows_cap, int cols_cap) {
+__host__ __device__ inline size_t smem_bytes(int rows_cap, int cols_cap, bool big = false) {
     size_t s = 0;
-    s += ((size_t)rows_cap * cols_cap + 2) * 8;    // cost block (+ slack: a row of the 1-D programme has cols + 1 entries)
+    // cost block (+ slack: a row of the 1-D programme has cols + 1 entries); BIG: that row only
+    s += big ? ((size_t)cols_cap + 2) * 8 : ((size_t)rows_cap * cols_cap + 2) * 8;
     s += (size_t)2 * (rows_cap + cols_cap) * 8;    // points S, T  (x, y)
     s += (size_t)(rows_cap + cols_cap) * 8;        // ds, dt
     s += (size_t)(rows_cap + 1) * 8;               // u
     s += (size_t)2 * (rows_cap + cols_cap + 1) * 8; // v, minv
     s += (size_t)2 * (rows_cap + cols_cap + 1) * 4; // p, way
+    if (big) s += (size_t)(rows_cap + cols_cap + 4);   // column-used flags
     return (s + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ double ground_cost(const double* S, const double* T, int i, int j) {
+    // L2 cost with sklearn's Gram trick: sqrt(max(|s|^2 - 2 s.t + |t|^2, 0))
+    const double sx = S[2 * i], sy = S[2 * i + 1], tx = T[2 * j], ty = T[2 * j + 1];
+    const double ns = __dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy));
+    const double nt = __dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty));
+    const double dot = fma(sy, ty, __dmul_rn(sx, tx));
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(-2.0, dot), ns), nt);
+    return sqrt(fmax(d2, 0.0));
 }
 
 // compact the finite rows of a diagram into (x, y) float64 pairs; empty -> one point (0,0)
@@ -86,13 +104,13 @@ __device__ int load_diagram(const TIn* __restrict__ bd, int n, int cap, double* 
     return m;
 }
 
-template <typename TIn>
+template <typename TIn, bool BIG>
 __global__ void __launch_bounds__(32) wasserstein_kernel(Params<TIn> p) {
     extern __shared__ __align__(16) unsigned char wsm[];
     const int lane = threadIdx.x;
     const int RC = p.rows_cap, CC = p.cols_cap;
     double* cost = (double*)wsm;
-    double* PA = cost + (size_t)RC * CC + 2;   // points of A, then points of B right behind them
+    double* PA = cost + (BIG ? (size_t)CC : (size_t)RC * CC) + 2;   // points of A, then points of B right behind them
     double* dS = PA + 2 * (size_t)(RC + CC);
     double* dT = dS + RC;
     double* u = dT + CC;
@@ -100,6 +118,7 @@ __global__ void __launch_bounds__(32) wasserstein_kernel(Params<TIn> p) {
     double* minv = v + (RC + CC + 1);
     int* pcol = (int*)(minv + (RC + CC + 1));
     int* way = pcol + (RC + CC + 1);
+    unsigned char* usedf = (unsigned char*)(way + (RC + CC + 1));   // BIG only
     const double cs = 0.7071067811865476, sn = 0.7071067811865475;  // np.cos(pi/4), np.sin(pi/4)
 
     for (long long k = blockIdx.x; k < p.B; k += gridDim.x) {
@@ -178,15 +197,11 @@ __global__ void __launch_bounds__(32) wasserstein_kernel(Params<TIn> p) {
                 continue;
             }
         }
-        // L2 costs with sklearn's Gram trick: sqrt(max(|s|^2 - 2 s.t + |t|^2, 0))
-        for (int e = lane; e < M * N; e += 32) {
-            const int i = e / N, j = e % N;
-            const double sx = S[2 * i], sy = S[2 * i + 1], tx = T[2 * j], ty = T[2 * j + 1];
-            const double ns = __dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy));
-            const double nt = __dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty));
-            const double dot = fma(sy, ty, __dmul_rn(sx, tx));
-            double d2 = __dadd_rn(__dadd_rn(__dmul_rn(-2.0, dot), ns), nt);
-            cost[(size_t)i * N + j] = sqrt(fmax(d2, 0.0));
+        if constexpr (!BIG) {
+            for (int e = lane; e < M * N; e += 32) {
+                const int i = e / N, j = e % N;
+                cost[(size_t)i * N + j] = ground_cost(S, T, i, j);
+            }
         }
         const int Mc = N + M;  // columns: N real + M private diagonal columns
         for (int j = lane; j <= Mc; j += 32) { v[j] = 0.0; pcol[j] = 0; }
@@ -197,19 +212,21 @@ __global__ void __launch_bounds__(32) wasserstein_kernel(Params<TIn> p) {
             if (lane == 0) pcol[0] = i;
             for (int j = lane; j <= Mc; j += 32) minv[j] = kInf;
             // used[] as a bitmask in registers: lane owns columns j = lane + 32 t
-            uint32_t used = 0;  // bit t <-> column lane + 32 t   (Mc <= 32*32)
+            uint32_t used = 0;  // bit t <-> column lane + 32 t   (Mc <= 32*32; BIG: byte flags in shared memory)
+            if constexpr (BIG) { for (int j = lane; j <= Mc; j += 32) usedf[j] = 0; }
             __syncwarp();
             int j0 = 0;
             while (true) {
-                if (lane == (j0 & 31)) used |= 1u << (j0 >> 5);
+                if constexpr (BIG) { if (lane == (j0 & 31)) usedf[j0] = 1; }
+                else { if (lane == (j0 & 31)) used |= 1u << (j0 >> 5); }
                 const int i0 = pcol[j0];
                 const double ui0 = u[i0];
                 double best = kInf;
                 int bestj = -1;
                 for (int j = lane, t = 0; j <= Mc; j += 32, ++t) {
-                    if (j == 0 || ((used >> t) & 1u)) continue;
+                    if (j == 0 || (BIG ? usedf[j] != 0 : ((used >> t) & 1u) != 0)) continue;
                     double a;
-                    if (j <= N) a = cost[(size_t)(i0 - 1) * N + (j - 1)] - dT[j - 1];
+                    if (j <= N) a = (BIG ? ground_cost(S, T, i0 - 1, j - 1) : cost[(size_t)(i0 - 1) * N + (j - 1)]) - dT[j - 1];
                     else a = (j - N == i0) ? dS[i0 - 1] : kInf;
                     const double cur = a - ui0 - v[j];
                     double mv = minv[j];
@@ -225,7 +242,7 @@ __global__ void __launch_bounds__(32) wasserstein_kernel(Params<TIn> p) {
                 }
                 const double delta = best;
                 for (int j = lane, t = 0; j <= Mc; j += 32, ++t) {
-                    if ((used >> t) & 1u) { u[pcol[j]] += delta; v[j] -= delta; }
+                    if (BIG ? usedf[j] != 0 : ((used >> t) & 1u) != 0) { u[pcol[j]] += delta; v[j] -= delta; }
                     else minv[j] -= delta;
                 }
                 __syncwarp();
@@ -243,7 +260,7 @@ __global__ void __launch_bounds__(32) wasserstein_kernel(Params<TIn> p) {
         double tot = 0.0;
         for (int j = lane + 1; j <= Mc; j += 32) {
             const int i = pcol[j];
-            if (j <= N) tot += (i > 0) ? cost[(size_t)(i - 1) * N + (j - 1)] : dT[j - 1];
+            if (j <= N) tot += (i > 0) ? (BIG ? ground_cost(S, T, i - 1, j - 1) : cost[(size_t)(i - 1) * N + (j - 1)]) : dT[j - 1];
             else if (i > 0) tot += dS[i - 1];
         }
 #pragma unroll
@@ -275,10 +292,12 @@ static int launch(const TIn* bdA, const int* nA, int nA_stride, int capA, int li
     const int ca = limA < 1 ? 1 : limA, cb = limB < 1 ? 1 : limB;
     p.rows_cap = ca < cb ? ca : cb;
     p.cols_cap = ca < cb ? cb : ca;
-    if (p.rows_cap + p.cols_cap + 1 > 1024) return TDA_E_SIZE;
-    const size_t smem = smem_bytes(p.rows_cap, p.cols_cap);
-    if (smem > 227 * 1024) return TDA_E_SIZE;
-    cudaError_t e = cudaFuncSetAttribute(wasserstein_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    size_t smem = smem_bytes(p.rows_cap, p.cols_cap);
+    const bool big = p.rows_cap + p.cols_cap + 1 > 1024 || smem > 227 * 1024;
+    if (big) smem = smem_bytes(p.rows_cap, p.cols_cap, true);
+    if (smem > 227 * 1024) return TDA_E_SIZE;   // more than ~4,000 points in a pair
+    cudaError_t e = big ? cudaFuncSetAttribute(wasserstein_kernel<TIn, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                        : cudaFuncSetAttribute(wasserstein_kernel<TIn, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -289,7 +308,8 @@ static int launch(const TIn* bdA, const int* nA, int nA_stride, int capA, int li
     long long grid = (long long)sms * per_sm;
     if (grid > B) grid = B;
     tda::ProfScope prof("wasserstein", (cudaStream_t)stream);
-    wasserstein_kernel<TIn><<<(int)grid, 32, smem, (cudaStream_t)stream>>>(p);
+    if (big) wasserstein_kernel<TIn, true><<<(int)grid, 32, smem, (cudaStream_t)stream>>>(p);
+    else wasserstein_kernel<TIn, false><<<(int)grid, 32, smem, (cudaStream_t)stream>>>(p);
     tda::count_launch();
     return (int)cudaGetLastError();
 }

@@ -97,3 +97,39 @@ def test_one_dimensional_pairs_take_the_dynamic_programme_and_agree(cuda):
         want = wasserstein_ref.wasserstein(A[k, :nA[k]].astype(np.float64), B[k, :nB[k]].astype(np.float64))
         assert abs(got[k] - want) <= 1e-9 * max(1.0, abs(want)), (k, got[k], want)
         assert abs(got2[k] - want) <= 1e-9 * max(1.0, abs(want)), (k, got2[k], want)
+
+
+def test_pairs_beyond_the_shared_memory_cost_block(cuda):
+    """Two diagrams of a few hundred points each (H1 of big clouds; H0 of two 248-point clouds) do not fit
+    the shared-memory cost block: the solver then evaluates the costs on the fly -- same arithmetic, so the
+    result must be the very number the cost-block variant gives where both apply, and scipy's otherwise."""
+    import torch
+    from oracle import wasserstein_ref
+    from tda_eeg_audio_b200.wasserstein import wasserstein, wasserstein_batched
+    rng = np.random.default_rng(7)
+    # (a) general pairs: 300 vs 420 points (1 MB of costs) and an H0-like 247 vs 247 (the dynamic programme)
+    K = 3
+    capA, capB = 300, 420
+    A = np.zeros((K, capA, 2), np.float32); B = np.zeros((K, capB, 2), np.float32)
+    nA = np.array([300, 0, 247], np.int32); nB = np.array([420, 57, 247], np.int32)
+    A[0] = _rand_dgm(rng, capA); B[0] = _rand_dgm(rng, capB, 0.8)
+    B[1, :57] = _rand_dgm(rng, 57)
+    A[2, :247, 1] = np.sort(rng.random(247)).astype(np.float32); B[2, :247, 1] = np.sort(rng.random(247) * 0.9).astype(np.float32)
+    got = wasserstein_batched(torch.from_numpy(A).cuda(), torch.from_numpy(nA).cuda(),
+                              torch.from_numpy(B).cuda(), torch.from_numpy(nB).cuda()).cpu().numpy()
+    for k in range(K):
+        want = wasserstein_ref.safe_wasserstein(A[k, :nA[k]].astype(np.float64), B[k, :nB[k]].astype(np.float64))
+        assert abs(got[k] - want) <= 1e-9 * max(1.0, abs(want)), (k, got[k], want)
+    # (b) bit-identical to the cost-block variant: the same small pair inside a batch with big caps and alone
+    a = _rand_dgm(rng, 40); b = _rand_dgm(rng, 90, 0.6)
+    A2 = np.zeros((1, 600, 2), np.float32); B2 = np.zeros((1, 600, 2), np.float32)
+    A2[0, :40] = a; B2[0, :90] = b
+    big = wasserstein_batched(torch.from_numpy(A2).cuda(), torch.tensor([40], dtype=torch.int32).cuda(),
+                              torch.from_numpy(B2).cuda(), torch.tensor([90], dtype=torch.int32).cuda()).item()
+    small = wasserstein_batched(torch.from_numpy(A2[:, :40].copy()).cuda(), torch.tensor([40], dtype=torch.int32).cuda(),
+                                torch.from_numpy(B2[:, :90].copy()).cuda(), torch.tensor([90], dtype=torch.int32).cuda()).item()
+    assert big == small
+    # (c) the float64 drop-in call on two large arbitrary diagrams
+    d1 = _rand_dgm(rng, 350).astype(np.float64) + 1e-9; d2 = _rand_dgm(rng, 280).astype(np.float64)
+    want = wasserstein_ref.safe_wasserstein(d1, d2)
+    assert abs(wasserstein(d1, d2) - want) <= 1e-9 * max(1.0, abs(want))
