@@ -273,8 +273,13 @@ __global__ void __launch_bounds__(kRankThreads, 1) rank_kernel(Params p) {
                 for (int i = 0; i < kRankPerThread; ++i) {
                     const int k = warp * (32 * kRankPerThread) + 32 * i + lane;
                     const bool act = k < nT;
-                    const uint32_t dg = act ? ((kr[i] >> sh) & 255u) : (256u + lane);   // idle lanes: no peers
-                    const uint32_t peers = __match_any_sync(kFull, dg);
+                    const uint32_t dg = (kr[i] >> sh) & 255u;
+                    uint32_t peers = __ballot_sync(kFull, act);   // (eight ballots instead of __match_any_sync, see rank_small_kernel)
+#pragma unroll
+                    for (int bt = 0; bt < 8; ++bt) {
+                        const uint32_t bal = __ballot_sync(kFull, (dg >> bt) & 1u);
+                        peers &= ((dg >> bt) & 1u) ? bal : ~bal;
+                    }
                     if (act) stage[rowc[dg] + __popc(peers & lt)] = make_uint2(kr[i], pr[i]);
                     __syncwarp();
                     if (act && (peers & lt) == 0) rowc[dg] += (uint16_t)__popc(peers);
@@ -433,8 +438,15 @@ __global__ void __launch_bounds__(NTH, MINB) rank_small_kernel(Params p) {
             for (int t = 0; t < EPT; ++t) {
                 const int k = seg0 + 32 * t + lane;
                 const bool act = t < nch && k < E;
-                const uint32_t dg = act ? ((kr[t] >> sh) & 255u) : (256u + lane);   // idle lanes: no peers
-                const uint32_t peers = __match_any_sync(kFull, dg);
+                // lanes with the same digit: eight ballots (one per digit bit).  __match_any_sync takes a step per
+                // distinct value, ~30 of them among 32 random digits, and was half of this kernel's stall samples
+                const uint32_t dg = (kr[t] >> sh) & 255u;
+                uint32_t peers = __ballot_sync(kFull, act);
+#pragma unroll
+                for (int bt = 0; bt < 8; ++bt) {
+                    const uint32_t bal = __ballot_sync(kFull, (dg >> bt) & 1u);
+                    peers &= ((dg >> bt) & 1u) ? bal : ~bal;
+                }
                 // the first lane of a digit group takes the group's slots from the warp's counter (one atomic on the
                 // packed pair of 16-bit counters: no carry, a cloud has fewer than 2^16 edges) and hands the old value
                 // on -- no read / barrier / write chain from one chunk to the next

@@ -1,8 +1,8 @@
 """Summarise one kernel of an ncu report as JSON (what profiles/*.json hold and bench.py's `ncu_capture` reads).
 
-    python tools/ncu_summary.py <report.ncu-rep> <units> "<command that produced it>" [unit-name] > profiles/<name>.json
+    python tools/ncu_summary.py <report.ncu-rep> <units> "<command that produced it>" [unit-name [k]] > profiles/<name>.json
 
-Uses `ncu -i <rep> --page raw --csv`; the first kernel in the report is summarised.  `units` = the
+Uses `ncu -i <rep> --page raw --csv`; the k-th kernel of the report (default: the first) is summarised.  `units` = the
 work units (windows, sequences, pairs ...) that launch processed, for the per-unit figures."""
 import csv
 import json
@@ -31,7 +31,7 @@ def main():
     unit_name = sys.argv[4] if len(sys.argv) > 4 else "window"
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    hdr, unit_row, vals = rows[0], rows[1], rows[2]
+    hdr, unit_row, vals = rows[0], rows[1], rows[2 + (int(sys.argv[5]) if len(sys.argv) > 5 else 0)]
     metrics, stalls = {}, {}
     for h, u, v in zip(hdr, unit_row, vals):
         if h in KEEP:
