@@ -108,3 +108,36 @@ def test_stress_cloud_against_oracle_with_pairs(cuda, n):
     c = orips.rips_h01_batched(D, 2.0, cap1=cap1)
     _assert_equal_diagrams(g, c, f"cloud{n}")
     assert c["counts"][0, 1] > 50
+
+
+def test_audio_sized_clouds_at_scale_bit_exact(cuda):
+    """The audio path (BASELINE configs[2]: Takens clouds of 97-248 points) at scale through the grid-wide
+    engine: 2,400 clouds with RAGGED point counts spread over the three shared-memory sort layouts (up to 128,
+    170 and 256 points), a quarter of them with distances quantised to 1/256 (long tie runs, which the bit-row
+    classification hands to the rank-row walk), pairs and float32 births / deaths bit-exact against the oracle."""
+    import torch
+    from oracle import rips as orips
+    from tda_eeg_audio_b200 import rips_h01_batched
+    from tests.test_rips_large_gpu import takens_like
+    rng = np.random.default_rng(2026)
+    total = 0
+    for N, lo, B in ((128, 66, 900), (170, 129, 700), (256, 171, 800)):
+        D = takens_like(rng, B, N)
+        D[::4] = np.round(D[::4] * 256) / 256
+        npts = rng.integers(lo, N + 1, B).astype(np.int32)
+        npts[:3] = [N, lo, N - 1]
+        cap1 = 1024
+        out = rips_h01_batched(torch.from_numpy(D).cuda(), thresh=2.0, cap1=cap1, want_pairs=True,
+                               npts=torch.from_numpy(npts).cuda(), engine="large")
+        torch.cuda.synchronize()
+        g = {k: v.cpu().numpy() for k, v in out.items() if k != "ws"}
+        assert not g["status"].any(), (N, np.nonzero(g["status"])[0][:10])
+        # the oracle takes one size per call: group the clouds by point count
+        for n in np.unique(npts):
+            sel = np.nonzero(npts == n)[0]
+            c = orips.rips_h01_batched(np.ascontiguousarray(D[sel][:, :n, :n]), 2.0, cap1=cap1)
+            gs = {"counts": g["counts"][sel], "bd0": g["bd0"][sel][:, :n], "pr0": g["pr0"][sel][:, :n],
+                  "bd1": g["bd1"][sel], "pr1": g["pr1"][sel]}
+            _assert_equal_diagrams(gs, c, f"N{N} n{n}")
+        total += B
+    assert total >= 2400
