@@ -129,190 +129,251 @@ template <typename TT> struct RankOf;
 template <> struct RankOf<uint16_t> { static constexpr uint32_t kAbsent = 0xFFFFu; };
 template <> struct RankOf<uint32_t> { static constexpr uint32_t kAbsent = 0xFFFFFFFFu; };
 
-// One CTA of 1,024 threads per cloud, one CTA per SM (the ping-pong arrays of the resident clouds stay
-// in L2).  A pass works through the array in tiles of 8,192 elements: every warp ranks its 256 elements
-// of the tile (a row of 16-bit digit counters per warp, __match_any_sync inside a chunk of 32), the tile
-// is staged in shared memory ordered by digit, and written out as runs (a digit's elements of one tile
-// are contiguous in the destination): full sectors instead of scattered 4-byte writes.
+// K1 for big clouds (257-2,048 points): a grid-wide sort of a GROUP of clouds at a time.  The sort arrays of a
+// 2,000-point cloud are 32 MB (keys and payloads, ping and pong): a CTA per cloud on every SM streams 4.7 GB of
+// them through DRAM four times, and scatters the ranks into 148 rank matrices at once, one 32-byte sector per
+// 4-byte write (measured: 94 GB of DRAM traffic for 148 clouds, 3x the algorithmic bytes, long-scoreboard stall
+// 54 cycles per issue).  Instead the whole grid works on as many clouds as fit the 126 MB L2 (three at 2,000
+// points): keys -> four passes of (per-tile digit histograms, stable scatter of staged tiles) -> P,
+// sorted keys and the rank matrix, every array of the group L2-resident from its first write to its last read.
+// A tile is 8,192 elements of one cloud: every warp ranks its 256 elements (a row of 16-bit digit counters per
+// warp, lanes with the same digit found by eight ballots), the tile is staged in shared memory ordered by digit
+// and written out as runs (a digit's elements of one tile are contiguous in the destination).
 constexpr int kRankThreads = 1024;
 constexpr int kRankWarps = kRankThreads / 32;
 constexpr int kRankPerThread = 8;
 constexpr int kRankTile = kRankThreads * kRankPerThread;
-constexpr size_t kRankSmem = (size_t)kRankTile * 8 + (size_t)kRankWarps * 256 * 2 + 4 * 256 * 4 + 64 * 4;
+constexpr size_t kRankSmem = (size_t)kRankTile * 8 + (size_t)kRankWarps * 256 * 2 + 2 * 256 * 4 + 64 * 4;
 
-template <typename TT>
-__global__ void __launch_bounds__(kRankThreads, 1) rank_kernel(Params p) {
+struct SortGroup {
+    int g0, G;          // clouds [g0, g0 + G) of the chunk
+    int ntiles;         // tiles per cloud (of the largest possible cloud)
+    uint32_t* hist;     // [G][ntiles][256]: digit counts of every tile
+};
+
+// keys in descending edge index: blockIdx.y = cloud of the group, the CTAs of a cloud stride over the 32 x 32 blocks
+// of the upper triangle.  A block is read by rows (lanes along i: 128-byte segments of D) and, transposed through
+// shared memory, written by columns (lanes along j: the position E - 1 - (C(i,2) + j) is consecutive in j), so
+// both sides move full sectors; lanes along i on the write side cost one sector per 4-byte store.
+__global__ void __launch_bounds__(kRankThreads) keys_big_kernel(Params p, SortGroup sg) {
+    __shared__ float tile[32][33];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = sg.g0 + blockIdx.y;
+    const int b = p.c0 + c;
+    const int n = cloud_n(p, b);
+    const int E = (int)c2(n);
+    uint32_t* kA = p.sortbuf + (size_t)c * 4 * p.Emax;
+    uint32_t* pA = kA + p.Emax;
+    const float* Db = p.D + (size_t)b * p.strideB;
+    const int nb = (n + 31) >> 5, nblk = nb * (nb + 1) / 2;
+    int valid = 0, nan_seen = 0;
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        // blk -> (bi, bj), bj <= bi: block row of the larger index, block column of the smaller
+        int bi = (int)((sqrtf(8.0f * (float)blk + 1.0f) - 1.0f) * 0.5f);
+        while ((bi + 1) * (bi + 2) / 2 <= blk) ++bi;
+        while (bi * (bi + 1) / 2 > blk) --bi;
+        const int bj = blk - bi * (bi + 1) / 2;
+        {
+            const int j = 32 * bj + warp, i = 32 * bi + lane;
+            float v = 0.0f;
+            if (j < i && i < n) v = __ldg(Db + (size_t)j * p.ld + i);
+            tile[warp][lane] = v;
+        }
+        __syncthreads();
+        {
+            const int i = 32 * bi + warp, j = 32 * bj + lane;
+            if (j < i && i < n) {
+                const float d = tile[lane][warp] + 0.0f;
+                nan_seen |= (d != d);
+                const bool ok = d <= p.thresh;
+                const int pos = E - 1 - (i * (i - 1) / 2 + j);
+                kA[pos] = ok ? float_key(d) : kInf;
+                pA[pos] = (uint32_t)j | ((uint32_t)i << 11);
+                valid += ok;
+            }
+        }
+        __syncthreads();
+    }
+    valid = __reduce_add_sync(kFull, valid);
+    nan_seen = __reduce_or_sync(kFull, nan_seen);
+    if (lane == 0) {
+        if (valid) atomicAdd(p.m + c, valid);
+        if (nan_seen) atomicOr(p.nanflag + c, 1);
+    }
+}
+
+// digit counts of one tile (blockIdx.x) of one cloud (blockIdx.y)
+__global__ void __launch_bounds__(kRankThreads) hist_big_kernel(Params p, SortGroup sg, int pass) {
+    __shared__ uint32_t h[256];
+    const int tid = threadIdx.x;
+    const int c = sg.g0 + blockIdx.y;
+    const int E = (int)c2(cloud_n(p, p.c0 + c));
+    const uint32_t* srcK = p.sortbuf + (size_t)c * 4 * p.Emax + ((pass & 1) ? 2 * p.Emax : 0);
+    const int sh = 8 * pass;
+    const int t0 = blockIdx.x * kRankTile;
+    if (tid < 256) h[tid] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kRankPerThread; ++i) {
+        const int k = t0 + i * kRankThreads + tid;
+        if (k < E) atomicAdd(&h[(srcK[k] >> sh) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid < 256) sg.hist[((size_t)blockIdx.y * sg.ntiles + blockIdx.x) * 256 + tid] = h[tid];
+}
+
+// stable scatter of one tile
+__global__ void __launch_bounds__(kRankThreads, 2) scatter_big_kernel(Params p, SortGroup sg, int pass) {
     constexpr int NTH = kRankThreads, NW = kRankWarps;
     extern __shared__ __align__(16) unsigned char rk_raw[];
     uint2* stage = reinterpret_cast<uint2*>(rk_raw);                                   // [kRankTile] (key, payload)
     uint16_t* wcnt = reinterpret_cast<uint16_t*>(rk_raw + (size_t)kRankTile * 8);       // [NW][256]
-    uint32_t* gbase = reinterpret_cast<uint32_t*>(wcnt + NW * 256);                     // [256] next free slot per digit
-    uint32_t* gofs = gbase + 256;                                                       // [256] global - local position
-    uint32_t* hist = gofs + 256;                                                        // [256]
-    uint32_t* spare = hist + 256;                                                       // [256]
+    uint32_t* gofs = reinterpret_cast<uint32_t*>(wcnt + NW * 256);                      // [256] global - local position
+    uint32_t* spare = gofs + 256;                                                       // [256]
     uint32_t* red = spare + 256;                                                        // [64]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = (1u << lane) - 1u;
-    for (int c = blockIdx.x; c < p.C; c += gridDim.x) {
-        const int b = p.c0 + c;
-        const int n = cloud_n(p, b);
-        const int E = (int)c2(n);
-        uint32_t* kA = p.sortbuf + (size_t)c * 4 * p.Emax;
-        uint32_t* pA = kA + p.Emax;
-        uint32_t* kB = pA + p.Emax;
-        uint32_t* pB = kB + p.Emax;
-        TT* Tc = reinterpret_cast<TT*>(p.T) + (size_t)c * p.N * p.ldT;
-        uint16_t* Qc = p.Q + (size_t)c * p.N * p.ldT;
-        const float* Db = p.D + (size_t)b * p.strideB;
-        // ---- tables of this cloud: T = absent, Q = none  (vectorised: ldT is a multiple of 32 entries)
-        {
-            uint4* t4 = reinterpret_cast<uint4*>(Tc);
-            const size_t nt4 = (size_t)n * p.ldT * sizeof(TT) / 16;
-            for (size_t q = tid; q < nt4; q += NTH) t4[q] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-            uint4* q4 = reinterpret_cast<uint4*>(Qc);
-            const size_t nq4 = (size_t)n * p.ldT * 2 / 16;
-            for (size_t q = tid; q < nq4; q += NTH) q4[q] = make_uint4(0u, 0u, 0u, 0u);
+    const int c = sg.g0 + blockIdx.y;
+    const int E = (int)c2(cloud_n(p, p.c0 + c));
+    const int t0 = blockIdx.x * kRankTile;
+    if (t0 >= E) return;
+    const int nT = E - t0 < kRankTile ? E - t0 : kRankTile;
+    uint32_t* base = p.sortbuf + (size_t)c * 4 * p.Emax;
+    const uint32_t* srcK = base + ((pass & 1) ? 2 * p.Emax : 0);
+    const uint32_t* srcP = srcK + p.Emax;
+    uint32_t* dstK = base + ((pass & 1) ? 0 : 2 * p.Emax);
+    uint32_t* dstP = dstK + p.Emax;
+    const int sh = 8 * pass;
+    // ---- where this tile's digits go: the elements of all lower digits of the cloud + those of the same digit in
+    //      earlier tiles.  A few threads per digit sum the tile counts (independent loads from L2, 62 k words per
+    //      cloud); no scan kernel between the histogram and the scatter
+    {
+        uint32_t* part = reinterpret_cast<uint32_t*>(stage);   // [2][<= 4][256], before the tile is staged
+        constexpr int TPD = NTH / 256;   // threads per digit
+        const int d = tid & 255, q = tid >> 8;
+        const uint32_t* hc = sg.hist + (size_t)blockIdx.y * sg.ntiles * 256;
+        uint32_t tot = 0, pre = 0;
+        for (int t = q; t < sg.ntiles; t += TPD) {
+            const uint32_t v = hc[(size_t)t * 256 + d];
+            tot += v;
+            if (t < (int)blockIdx.x) pre += v;
         }
-        // ---- keys in descending edge index (a warp per matrix row, lanes along the row: coalesced reads)
-        int valid = 0, nan_seen = 0;
-        uint32_t k_or = 0, k_and = 0xFFFFFFFFu;
-        for (int j = warp; j < n - 1; j += NW) {
-            const float* row = Db + (size_t)j * p.ld;
-            for (int i = j + 1 + lane; i < n; i += 32) {
-                const float d = row[i] + 0.0f;
-                nan_seen |= (d != d);
-                const bool ok = d <= p.thresh;
-                const uint32_t key = ok ? float_key(d) : kInf;
-                const int pos = E - 1 - ((int)c2(i) + j);
-                kA[pos] = key;
-                pA[pos] = (uint32_t)j | ((uint32_t)i << 11);
-                if (ok) { ++valid; k_or |= key; k_and &= key; }
+        part[q * 256 + d] = tot;
+        part[1024 + q * 256 + d] = pre;
+        __syncthreads();
+        if (tid < 256) {
+            tot = 0; pre = 0;
+#pragma unroll
+            for (int k = 0; k < TPD; ++k) { tot += part[k * 256 + tid]; pre += part[1024 + k * 256 + tid]; }
+            uint32_t incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += y;
             }
-        }
-        valid = __reduce_add_sync(kFull, valid);
-        nan_seen = __reduce_or_sync(kFull, nan_seen);
-        k_or = __reduce_or_sync(kFull, k_or);
-        k_and = __reduce_and_sync(kFull, k_and);
-        __syncthreads();   // red[] of the previous cloud has been read
-        if (lane == 0) { red[warp] = (uint32_t)valid; spare[warp] = k_or; spare[NW + warp] = k_and; spare[2 * NW + warp] = (uint32_t)nan_seen; }
-        __syncthreads();   // ... and kA / pA are complete
-        int m = 0;
-        uint32_t vor = 0, vand = 0xFFFFFFFFu, any_nan = 0;
-        for (int w = 0; w < NW; ++w) { m += (int)red[w]; vor |= spare[w]; vand &= spare[NW + w]; any_nan |= spare[2 * NW + w]; }
-        // with absent edges (d > thresh, NaN) in between every pass runs: they have to travel to the end
-        const uint32_t varying = (m < E) ? 0xFFFFFFFFu : (vor ^ vand);
-        uint32_t* srcK = kA; uint32_t* srcP = pA; uint32_t* dstK = kB; uint32_t* dstP = pB;
-        for (int pass = 0; pass < 4; ++pass) {
-            const int sh = 8 * pass;
-            if (!((varying >> sh) & 255u)) continue;
-            // ---- digit histogram of the whole array -> first free slot of every digit
-            __syncthreads();
-            if (tid < 256) hist[tid] = 0;
-            __syncthreads();
-            for (int k = tid; k < E; k += NTH) atomicAdd(&hist[(srcK[k] >> sh) & 255u], 1u);
-            __syncthreads();
-            if (tid < 256) {
-                const uint32_t own = hist[tid];
-                uint32_t incl = own;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t y = __shfl_up_sync(kFull, incl, o);
-                    if (lane >= o) incl += y;
-                }
-                if (lane == 31) red[32 + warp] = incl;
-                asm volatile("bar.sync 1, 256;");       // the eight scanning warps only
-                uint32_t base = 0;
-                for (int w = 0; w < warp; ++w) base += red[32 + w];
-                gbase[tid] = base + incl - own;
-            }
-            __syncthreads();
-            for (int t0 = 0; t0 < E; t0 += kRankTile) {
-                const int nT = E - t0 < kRankTile ? E - t0 : kRankTile;
-                // ---- this warp's 256 elements of the tile, their digits counted into its counter row
-                uint32_t* wc32 = reinterpret_cast<uint32_t*>(wcnt);
-                for (int q = tid; q < NW * 128; q += NTH) wc32[q] = 0;
-                __syncthreads();
-                uint32_t kr[kRankPerThread], pr[kRankPerThread];
-                uint32_t* row32 = wc32 + warp * 128;
-#pragma unroll
-                for (int i = 0; i < kRankPerThread; ++i) {
-                    const int k = warp * (32 * kRankPerThread) + 32 * i + lane;
-                    const bool act = k < nT;
-                    kr[i] = act ? srcK[t0 + k] : 0u;
-                    pr[i] = act ? srcP[t0 + k] : 0u;
-                    if (act) {
-                        const uint32_t dg = (kr[i] >> sh) & 255u;
-                        atomicAdd(row32 + (dg >> 1), 1u << (16 * (dg & 1u)));
-                    }
-                }
-                __syncthreads();
-                // ---- local slot of (digit, warp): exclusive scan in digit-major order
-                if (tid < 256) {
-                    uint32_t run = 0;
-                    for (int w = 0; w < NW; ++w) { const uint32_t t = wcnt[w * 256 + tid]; wcnt[w * 256 + tid] = (uint16_t)run; run += t; }
-                    uint32_t incl = run;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t y = __shfl_up_sync(kFull, incl, o);
-                        if (lane >= o) incl += y;
-                    }
-                    if (lane == 31) red[32 + warp] = incl;
-                    asm volatile("bar.sync 1, 256;");
-                    uint32_t tstart = 0;
-                    for (int w = 0; w < warp; ++w) tstart += red[32 + w];
-                    tstart += incl - run;
-                    for (int w = 0; w < NW; ++w) wcnt[w * 256 + tid] += (uint16_t)tstart;
-                    gofs[tid] = gbase[tid] - tstart;
-                    gbase[tid] += run;
-                    asm volatile("bar.sync 1, 256;");   // red[32..40) is read before the next tile rewrites it
-                }
-                __syncthreads();
-                // ---- stage the tile in digit order (stable: chunks in order, lanes ranked inside a chunk)
-                uint16_t* rowc = wcnt + warp * 256;
-#pragma unroll
-                for (int i = 0; i < kRankPerThread; ++i) {
-                    const int k = warp * (32 * kRankPerThread) + 32 * i + lane;
-                    const bool act = k < nT;
-                    const uint32_t dg = (kr[i] >> sh) & 255u;
-                    uint32_t peers = __ballot_sync(kFull, act);   // (eight ballots instead of __match_any_sync, see rank_small_kernel)
-#pragma unroll
-                    for (int bt = 0; bt < 8; ++bt) {
-                        const uint32_t bal = __ballot_sync(kFull, (dg >> bt) & 1u);
-                        peers &= ((dg >> bt) & 1u) ? bal : ~bal;
-                    }
-                    if (act) stage[rowc[dg] + __popc(peers & lt)] = make_uint2(kr[i], pr[i]);
-                    __syncwarp();
-                    if (act && (peers & lt) == 0) rowc[dg] += (uint16_t)__popc(peers);
-                    __syncwarp();
-                }
-                __syncthreads();
-                // ---- write the tile out: a digit's elements are a contiguous run in the destination
-                for (int lp = tid; lp < nT; lp += NTH) {
-                    const uint2 e = stage[lp];
-                    const uint32_t g = gofs[(e.x >> sh) & 255u] + lp;
-                    dstK[g] = e.x;
-                    dstP[g] = e.y;
-                }
-                __syncthreads();
-            }
-            uint32_t* t;
-            t = srcK; srcK = dstK; dstK = t;
-            t = srcP; srcP = dstP; dstP = t;
+            if (lane == 31) red[warp] = incl;
+            asm volatile("bar.sync 1, 256;");
+            uint32_t dbase = incl - tot;
+            for (int w = 0; w < warp; ++w) dbase += red[w];
+            spare[tid] = dbase + pre;
         }
         __syncthreads();
-        // ---- sorted position -> P, T, sorted keys
-        uint32_t* Pc = p.P + (size_t)c * p.Emax;
-        uint32_t* sk = p.skey + (size_t)c * p.Emax;
-        for (int r = tid; r < m; r += NTH) {
-            const uint32_t key = srcK[r], pay = srcP[r];
+    }
+    // ---- this warp's 256 elements of the tile, their digits counted into its counter row
+    uint32_t* wc32 = reinterpret_cast<uint32_t*>(wcnt);
+    for (int q = tid; q < NW * 128; q += NTH) wc32[q] = 0;
+    __syncthreads();
+    uint32_t kr[kRankPerThread], pr[kRankPerThread];
+    uint32_t* row32 = wc32 + warp * 128;
+#pragma unroll
+    for (int i = 0; i < kRankPerThread; ++i) {
+        const int k = warp * (32 * kRankPerThread) + 32 * i + lane;
+        const bool act = k < nT;
+        kr[i] = act ? srcK[t0 + k] : 0u;
+        pr[i] = act ? srcP[t0 + k] : 0u;
+        if (act) {
+            const uint32_t dg = (kr[i] >> sh) & 255u;
+            atomicAdd(row32 + (dg >> 1), 1u << (16 * (dg & 1u)));
+        }
+    }
+    __syncthreads();
+    // ---- local slot of (digit, warp): exclusive scan in digit-major order
+    if (tid < 256) {
+        uint32_t run = 0;
+        for (int w = 0; w < NW; ++w) { const uint32_t t = wcnt[w * 256 + tid]; wcnt[w * 256 + tid] = (uint16_t)run; run += t; }
+        uint32_t incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) red[32 + warp] = incl;
+        asm volatile("bar.sync 1, 256;");       // the eight scanning warps only
+        uint32_t tstart = 0;
+        for (int w = 0; w < warp; ++w) tstart += red[32 + w];
+        tstart += incl - run;
+        for (int w = 0; w < NW; ++w) wcnt[w * 256 + tid] += (uint16_t)tstart;
+        gofs[tid] = spare[tid] - tstart;
+    }
+    __syncthreads();
+    // ---- stage the tile in digit order (stable: chunks in order, lanes ranked inside a chunk)
+    uint16_t* rowc = wcnt + warp * 256;
+#pragma unroll
+    for (int i = 0; i < kRankPerThread; ++i) {
+        const int k = warp * (32 * kRankPerThread) + 32 * i + lane;
+        const bool act = k < nT;
+        const uint32_t dg = (kr[i] >> sh) & 255u;
+        uint32_t peers = __ballot_sync(kFull, act);   // (eight ballots instead of __match_any_sync, see rank_small_kernel)
+#pragma unroll
+        for (int bt = 0; bt < 8; ++bt) {
+            const uint32_t bal = __ballot_sync(kFull, (dg >> bt) & 1u);
+            peers &= ((dg >> bt) & 1u) ? bal : ~bal;
+        }
+        if (act) stage[rowc[dg] + __popc(peers & lt)] = make_uint2(kr[i], pr[i]);
+        __syncwarp();
+        if (act && (peers & lt) == 0) rowc[dg] += (uint16_t)__popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    // ---- write the tile out: a digit's elements are a contiguous run in the destination
+    for (int lp = tid; lp < nT; lp += NTH) {
+        const uint2 e = stage[lp];
+        const uint32_t g = gofs[(e.x >> sh) & 255u] + lp;
+        dstK[g] = e.x;
+        dstP[g] = e.y;
+    }
+}
+
+// sorted position -> P, sorted keys, rank matrix (every entry of a row is written here: present edges by rank,
+// absent ones, the diagonal and the padding as "absent" -- full sectors, the matrices of the group stay in L2)
+__global__ void __launch_bounds__(kRankThreads) finish_big_kernel(Params p, SortGroup sg) {
+    const int tid = threadIdx.x;
+    const int c = sg.g0 + blockIdx.y;
+    const int n = cloud_n(p, p.c0 + c);
+    const int E = (int)c2(n);
+    const int m = n >= 2 ? p.m[c] : 0;
+    const uint32_t* srcK = p.sortbuf + (size_t)c * 4 * p.Emax;   // four passes: back in the first pair of arrays
+    const uint32_t* srcP = srcK + p.Emax;
+    uint32_t* Pc = p.P + (size_t)c * p.Emax;
+    uint32_t* sk = p.skey + (size_t)c * p.Emax;
+    uint32_t* Tc = reinterpret_cast<uint32_t*>(p.T) + (size_t)c * p.N * p.ldT;
+    for (int r = blockIdx.x * kRankThreads + tid; r < E; r += gridDim.x * kRankThreads) {
+        const uint32_t key = srcK[r], pay = srcP[r];
+        const int i = (int)(pay >> 11), j = (int)(pay & 2047u);
+        const uint32_t val = r < m ? (uint32_t)r : 0xFFFFFFFFu;
+        if (r < m) {
             const bool tie = r + 1 < m && srcK[r + 1] == key;
-            const int i = (int)(pay >> 11), j = (int)(pay & 2047u);
             Pc[r] = pay | (tie ? kTieNext : 0u);
             sk[r] = key;
-            Tc[(size_t)i * p.ldT + j] = (TT)r;
-            Tc[(size_t)j * p.ldT + i] = (TT)r;
         }
-        if (tid == 0) { p.m[c] = n >= 2 ? m : 0; p.nanflag[c] = any_nan ? 1 : 0; }
+        Tc[(size_t)i * p.ldT + j] = val;
+        Tc[(size_t)j * p.ldT + i] = val;
+    }
+    // diagonal and padding
+    const int padw = p.ldT - n + 1;   // per row: the diagonal entry + the columns n .. ldT - 1
+    for (int q = blockIdx.x * kRankThreads + tid; q < n * padw; q += gridDim.x * kRankThreads) {
+        const int i = q / padw, k = q - i * padw;
+        Tc[(size_t)i * p.ldT + (k == 0 ? i : n + k - 1)] = 0xFFFFFFFFu;
     }
 }
 
@@ -1112,7 +1173,7 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
         int qa[APT], qb[APT];
         // apex of (thread, h): four CONSECUTIVE apexes per thread when the ranks are 16-bit (clouds up to
         // 256 points: NTH * 4 covers the padded row), so each of the four rows is one 8-byte load per thread;
-        // the padding of a row is "absent" in T and 0 in Q (rank_kernel), no bounds test needed
+        // the padding of a row is "absent" in T and 0 in Q (rank_small_kernel), no bounds test needed
         constexpr bool kVec = sizeof(TT) == 2 && (APT == 4 || APT == 8);
         if constexpr (kVec) {
             // APT consecutive apexes per thread: each of the four rows is one 8- or 16-byte load per thread
@@ -1393,7 +1454,8 @@ struct Plan {
     int N, ldT, ib, C, grid1, grid2, nth, apt, capP, capR;
     long long Emax;
     int tbytes;   // bytes per rank of T: 2 up to 256 points, else 4
-    size_t sortbuf, skey, P, T, Q, defv, m, nanflag, counters, nbirth, order, list, list0, phic1, phic2, pcr, act, rec, sglob, total;
+    size_t sortbuf, skey, P, T, Q, defv, m, nanflag, counters, nbirth, order, list, list0, phic1, phic2, pcr, act, rec, sglob, sorthist, total;
+    int sortG, ntiles;   // big clouds: clouds per sort group (their sort arrays fit L2), tiles per cloud
 };
 static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 static int bits_for(long long v) { int b = 1; while ((1ll << b) < v) ++b; return b; }
@@ -1452,6 +1514,15 @@ static bool make_plan(int B, int N, size_t ws_bytes, Plan& pl) {
         pl.act = o; o += al((size_t)pl.grid1 * pl.Emax * 4);
         pl.rec = o; o += al((size_t)pl.grid1 * 3 * pl.capR * 4);
         pl.sglob = o; o += al((size_t)pl.grid2 * N * 32 * 4);
+        pl.sorthist = o;
+        pl.ntiles = (int)((pl.Emax + kRankTile - 1) / kRankTile);
+        pl.sortG = 1;
+        if (N > 256) {
+            long long g = ((long long)96 << 20) / (16 * pl.Emax);   // 16 bytes of sort arrays per edge, 96 of the 126 MB of L2
+            pl.sortG = (int)(g < 1 ? 1 : (g > 64 ? 64 : g));
+            if (pl.sortG > C) pl.sortG = C;
+            o += al((size_t)pl.sortG * pl.ntiles * 256 * 4);
+        }
         pl.total = o;
     };
     long long C = B < cmax ? B : cmax;
@@ -1568,9 +1639,29 @@ extern "C" int tda_rips_h01_large(const float* D, const int* npts, int B, int N,
             else if (N <= 170) e = launch_rank_small<512, 32, 2>(p, st);     // E <= 14,365, T <= 64 KB: two
             else if (N <= 256) e = launch_rank_small<1024, 32, 1>(p, st);    // E <= 32,640: 209 KB, one
             else {
-                cudaFuncSetAttribute(rank_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRankSmem);
-                rank_kernel<uint32_t><<<grid, kRankThreads, kRankSmem, st>>>(p);
-                e = cudaSuccess;
+                // the grid-wide sort, a group of clouds at a time (their arrays stay in L2 from the keys to the rank matrix)
+                if ((e = cudaMemsetAsync(w8 + pl.m, 0, pl.list - pl.m, st)) != cudaSuccess) return (int)e;   // m, nanflag
+                if ((e = cudaMemsetAsync(w8 + pl.Q, 0, (size_t)C * N * pl.ldT * 2, st)) != cudaSuccess) return (int)e;
+                cudaFuncSetAttribute(scatter_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRankSmem);
+                SortGroup sg;
+                sg.ntiles = pl.ntiles;
+                sg.hist = (uint32_t*)(w8 + pl.sorthist);
+                for (int g0 = 0; g0 < C; g0 += pl.sortG) {
+                    sg.g0 = g0;
+                    sg.G = (C - g0) < pl.sortG ? (C - g0) : pl.sortG;
+                    int gx = (2 * kSms + sg.G - 1) / sg.G;   // CTAs per cloud for the block- and rank-strided kernels
+                    { const int nb = (N + 31) / 32; if (gx > nb * (nb + 1) / 2) gx = nb * (nb + 1) / 2; }
+                    keys_big_kernel<<<dim3(gx, sg.G), kRankThreads, 0, st>>>(p, sg);
+                    for (int pass = 0; pass < 4; ++pass) {
+                        hist_big_kernel<<<dim3(pl.ntiles, sg.G), kRankThreads, 0, st>>>(p, sg, pass);
+                        scatter_big_kernel<<<dim3(pl.ntiles, sg.G), kRankThreads, kRankSmem, st>>>(p, sg, pass);
+                    }
+                    int gf = (2 * kSms + sg.G - 1) / sg.G;
+                    if (gf > pl.ntiles * 8) gf = pl.ntiles * 8;
+                    finish_big_kernel<<<dim3(gf, sg.G), kRankThreads, 0, st>>>(p, sg);
+                    count_launch(10);
+                }
+                e = cudaGetLastError();
             }
             if (e != cudaSuccess) return (int)e;
             count_launch();
