@@ -59,6 +59,8 @@ constexpr uint32_t kTieNext = 1u << 23;  // the next edge in the order has the s
 constexpr uint32_t kBirth = 1u << 24;    // gives birth to an H1 class
 constexpr int kCapPMax = 65534;          // compact PHI entries per cloud (Q is u16, 0 = none)
 constexpr int kCapRMax = 65536;          // death records per cloud
+constexpr int kLevels = 6;               // early adjacency snapshots of a big cloud: after m/128, m/64, ... m/4 edges
+constexpr int kLevWords = 2048 / 32;     // words per bit row (kMaxN vertices)
 
 __host__ __device__ inline long long c2(long long i) { return i * (i - 1) / 2; }
 __host__ __device__ inline long long c3(long long i) { return i * (i - 1) * (i - 2) / 6; }
@@ -117,6 +119,9 @@ struct Params {
     int* queue;         // next position of the current sweep launch
     const int* order;   // position -> cloud, heaviest first (nullptr: positions are clouds)
     int* nbirth;        // [C] number of H1 births of every cloud (classify), the weight behind `order`
+    // big clouds: adjacency bit rows at six early ranks (classification of the early edges)
+    const uint32_t* lev;   // [C][kLevels][N][kLevWords]; nullptr: none
+    const int* levR;       // [C][2 kLevels]: the level ranks, then the same extended to the end of their tie runs
 };
 
 __device__ __forceinline__ int cloud_n(const Params& p, int b) {
@@ -374,6 +379,55 @@ __global__ void __launch_bounds__(kRankThreads) finish_big_kernel(Params p, Sort
     for (int q = blockIdx.x * kRankThreads + tid; q < n * padw; q += gridDim.x * kRankThreads) {
         const int i = q / padw, k = q - i * padw;
         Tc[(size_t)i * p.ldT + (k == 0 ? i : n + k - 1)] = 0xFFFFFFFFu;
+    }
+}
+
+// Adjacency bit rows of a big cloud after its first m/128, m/64, ... m/4 edges (each rank extended to the end of
+// its tie run), from the rank matrix while it is still L2-resident.  The classification walks two rank rows per
+// edge from the largest apex down until it finds a cofacet: late edges find one within a step or two, but an
+// early edge -- the graph is sparse, there is often none -- walks the whole of both rows (8 KB each), and those
+// few per cent of the edges were most of the classification's traffic.  With the rows of the first level above
+// its rank an early edge looks at the handful of common neighbours instead.
+__global__ void __launch_bounds__(256) levels_big_kernel(Params p, SortGroup sg, uint32_t* lev, int* levR) {
+    __shared__ int R[kLevels];
+    const int c = sg.g0 + blockIdx.y;
+    const int n = cloud_n(p, p.c0 + c);
+    const int m = n >= 2 ? p.m[c] : 0;
+    const uint32_t* sk = p.skey + (size_t)c * p.Emax;
+    if (threadIdx.x < kLevels) {
+        int r = m >> (7 - threadIdx.x);
+        const int r_lev = r;
+        while (r > 0 && r < m && sk[r] == sk[r - 1]) ++r;   // to the end of the tie run that holds rank r - 1
+        R[threadIdx.x] = r;
+        if (blockIdx.x == 0) { levR[c * 2 * kLevels + threadIdx.x] = r_lev; levR[c * 2 * kLevels + kLevels + threadIdx.x] = r; }
+    }
+    __syncthreads();
+    uint32_t rl[kLevels];
+#pragma unroll
+    for (int k = 0; k < kLevels; ++k) rl[k] = (uint32_t)R[k];
+    const uint32_t* Tc = reinterpret_cast<const uint32_t*>(p.T) + (size_t)c * p.N * p.ldT;
+    uint32_t* L = lev + (size_t)c * kLevels * p.N * kLevWords;
+    const int nwt = p.ldT >> 5;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n * kLevWords; idx += gridDim.x * blockDim.x) {
+        const int v = idx / kLevWords, w = idx - v * kLevWords;
+        uint32_t bits[kLevels];
+#pragma unroll
+        for (int k = 0; k < kLevels; ++k) bits[k] = 0;
+        if (w < nwt) {
+            const uint4* t4 = reinterpret_cast<const uint4*>(Tc + (size_t)v * p.ldT + 32 * w);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const uint4 t = t4[q];
+                const uint32_t tt[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+#pragma unroll
+                    for (int k = 0; k < kLevels; ++k) bits[k] |= (uint32_t)(tt[e] < rl[k]) << (4 * q + e);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kLevels; ++k) L[(size_t)(k * p.N + v) * kLevWords + w] = bits[k];
     }
 }
 
@@ -710,6 +764,45 @@ __global__ void __launch_bounds__(256) classify_kernel(Params p) {
         const uint4* Tj = reinterpret_cast<const uint4*>(Tc + (size_t)j * p.ldT);
         int dv = -1;
         bool found = false;
+        if constexpr (sizeof(TT) == 4 && !ONLY_TIED) {
+            // an early edge of a big cloud: candidates = common neighbours in the bit rows of the first level above
+            // its rank (a superset of its apexes, tie run included), largest first, each checked on the ranks
+            int lv = -1;
+            if (p.lev) {
+                const int* R = p.levR + c * 2 * kLevels;
+#pragma unroll
+                for (int k = kLevels - 1; k >= 0; --k) if (r < R[k]) lv = k;
+            }
+            if (lv >= 0) {
+                const uint32_t* Lc = p.lev + ((size_t)c * kLevels + lv) * p.N * kLevWords;
+                const uint4* ai = reinterpret_cast<const uint4*>(Lc + (size_t)i * kLevWords);
+                const uint4* aj = reinterpret_cast<const uint4*>(Lc + (size_t)j * kLevWords);
+                const uint32_t* Ti32 = reinterpret_cast<const uint32_t*>(Tc + (size_t)i * p.ldT);
+                const uint32_t* Tj32 = reinterpret_cast<const uint32_t*>(Tc + (size_t)j * p.ldT);
+                for (int w4 = (n - 1) >> 7; w4 >= 0 && !found; --w4) {
+                    const uint4 a = __ldg(ai + w4), b = __ldg(aj + w4);
+                    const uint32_t cm[4] = {a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w};
+#pragma unroll
+                    for (int k = 3; k >= 0; --k) {
+                        uint32_t word = cm[k];
+                        while (word && !found) {
+                            const int bit = 31 - __clz(word);
+                            word &= ~(1u << bit);
+                            const int v = 32 * (4 * w4 + k) + bit;
+                            const uint32_t ta = __ldg(Ti32 + v), tb = __ldg(Tj32 + v);
+                            bool ina = ta < (uint32_t)r, inb = tb < (uint32_t)r;
+                            const bool strict = ina && inb;
+                            if (tied) {
+                                if (!ina && ta != kAbsent && ta > (uint32_t)r) ina = keys[ta] == k32r;
+                                if (!inb && tb != kAbsent && tb > (uint32_t)r) inb = keys[tb] == k32r;
+                            }
+                            if (ina && inb) { found = true; dv = strict ? v : -1; }
+                        }
+                    }
+                }
+                found = true;   // (no candidate left: a birth)
+            }
+        }
         for (int vb = (n - 1) / VPL; vb >= 0 && !found; --vb) {
             const uint4 a4 = __ldg(Ti + vb), b4 = __ldg(Tj + vb);
             const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w}, bw[4] = {b4.x, b4.y, b4.z, b4.w};
@@ -1454,7 +1547,7 @@ struct Plan {
     int N, ldT, ib, C, grid1, grid2, nth, apt, capP, capR;
     long long Emax;
     int tbytes;   // bytes per rank of T: 2 up to 256 points, else 4
-    size_t sortbuf, skey, P, T, Q, defv, m, nanflag, counters, nbirth, order, list, list0, phic1, phic2, pcr, act, rec, sglob, sorthist, total;
+    size_t sortbuf, skey, P, T, Q, defv, m, nanflag, counters, nbirth, order, list, list0, phic1, phic2, pcr, act, rec, sglob, sorthist, lev, levR, total;
     int sortG, ntiles;   // big clouds: clouds per sort group (their sort arrays fit L2), tiles per cloud
 };
 static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -1522,6 +1615,8 @@ static bool make_plan(int B, int N, size_t ws_bytes, Plan& pl) {
             pl.sortG = (int)(g < 1 ? 1 : (g > 64 ? 64 : g));
             if (pl.sortG > C) pl.sortG = C;
             o += al((size_t)pl.sortG * pl.ntiles * 256 * 4);
+            pl.lev = o; o += al((size_t)C * kLevels * N * kLevWords * 4);
+            pl.levR = o; o += al((size_t)C * 2 * kLevels * 4);
         }
         pl.total = o;
     };
@@ -1626,6 +1721,8 @@ extern "C" int tda_rips_h01_large(const float* D, const int* npts, int B, int N,
     p.rec = (uint32_t*)(w8 + pl.rec); p.sglob = (uint32_t*)(w8 + pl.sglob);
     p.worklist = nullptr; p.n_work = nullptr; p.overflow_list = nullptr; p.n_overflow = nullptr;
     p.queue = nullptr; p.order = nullptr; p.nbirth = (int*)(w8 + pl.nbirth);
+    p.lev = N > 256 ? (const uint32_t*)(w8 + pl.lev) : nullptr;
+    p.levR = N > 256 ? (const int*)(w8 + pl.levR) : nullptr;
     cudaError_t e;
     for (int c0 = 0; c0 < B; c0 += pl.C) {
         const int C = (B - c0) < pl.C ? (B - c0) : pl.C;
@@ -1659,7 +1756,8 @@ extern "C" int tda_rips_h01_large(const float* D, const int* npts, int B, int N,
                     int gf = (2 * kSms + sg.G - 1) / sg.G;
                     if (gf > pl.ntiles * 8) gf = pl.ntiles * 8;
                     finish_big_kernel<<<dim3(gf, sg.G), kRankThreads, 0, st>>>(p, sg);
-                    count_launch(10);
+                    levels_big_kernel<<<dim3(gf, sg.G), 256, 0, st>>>(p, sg, (uint32_t*)(w8 + pl.lev), (int*)(w8 + pl.levR));
+                    count_launch(11);
                 }
                 e = cudaGetLastError();
             }
