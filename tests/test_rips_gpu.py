@@ -254,3 +254,36 @@ def test_known_answers_from_theory(cuda):
             check(name, Dg, thr, h0, h1)
             check(name + "/condensed", condense(Dg), thr, h0, h1, n_points=n)
         check(name + "/large", Dg, thr, h0, h1, engine="large")
+
+
+def test_host_entry_points_on_two_devices_in_one_process(cuda):
+    """The *_host entry points cache staging buffers and streams per device ordinal: one process calling
+    with device 0, then 1, then 0 again must get the same bits from each (skipped on a one-GPU box)."""
+    import torch
+    from tda_eeg_audio_b200 import _lib
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    D = inputs.eeg_like(np.random.default_rng(12), 2000)
+    B, n, cap1 = len(D), 47, 64
+    outs = []
+    for dev in (0, 1, 0):
+        bd0 = np.zeros((B, n, 2), np.float32); pr0 = np.zeros((B, n, 2), np.int64)
+        bd1 = np.zeros((B, cap1, 2), np.float32); pr1 = np.zeros((B, cap1, 2), np.int64)
+        counts = np.zeros((B, 2), np.int32); status = np.zeros(B, np.int32)
+        rc = _lib.load().tda_rips_h01_host(D.ctypes.data, B, n, 2.0, bd0.ctypes.data, pr0.ctypes.data,
+                                           bd1.ctypes.data, pr1.ctypes.data, counts.ctypes.data, cap1,
+                                           status.ctypes.data, dev)
+        assert rc == 0, (dev, rc)
+        outs.append((bd0, pr0, bd1, pr1, counts, status))
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert np.array_equal(a, b)
+    feats = []
+    for dev in (1, 0):
+        table = np.zeros((2, 5 * 44)); f = np.zeros((B, 2, 11))
+        D5 = np.ascontiguousarray(D[:600].reshape(2, 5, 60, n, n))
+        rc = _lib.load().tda_eeg_features_host(D5.ctypes.data, 2, 5, 60, n, 2.0, 128, None, None, None, None,
+                                               f.ctypes.data, table.ctypes.data, dev)
+        assert rc == 0, (dev, rc)
+        feats.append(table)
+    assert np.array_equal(feats[0], feats[1])
