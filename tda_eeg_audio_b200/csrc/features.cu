@@ -141,16 +141,13 @@ extern "C" int tda_pers_features(const float* bd, int cap, const int* counts, in
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const bool small = cap <= 128;   // EEG-window diagrams: sixteen lanes each; big diagrams keep a warp each
-    long long need = ((long long)B + (small ? 15 : 7)) / (small ? 16 : 8);
+    // sixteen lanes per diagram whatever its size: the summation order, and with it the last bits of the features,
+    // must not depend on the padding `cap` the caller happened to choose
+    long long need = ((long long)B + 15) / 16;
     int grid = (int)(need < (long long)sms * 8 ? need : (long long)sms * 8);
     tda::ProfScope prof("pers_features", (cudaStream_t)stream);
-    if (small)
-        tda::features::pers_features_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(bd, cap, counts, count_stride, B,
-                                                                                        feats, feat_stride);
-    else
-        tda::features::pers_features_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(bd, cap, counts, count_stride, B,
-                                                                                        feats, feat_stride);
+    tda::features::pers_features_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(bd, cap, counts, count_stride, B,
+                                                                                    feats, feat_stride);
     tda::count_launch();
     return (int)cudaGetLastError();
 }

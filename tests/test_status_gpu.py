@@ -64,7 +64,7 @@ def test_wasserstein_float64_and_safe_semantics(cuda):
     assert abs(safe_wasserstein(a, np.vstack([b, [[0.2, np.inf]]])) - ref) <= 1e-12 * max(ref, 1.0)
     assert np.isnan(safe_wasserstein(np.zeros((3, 3)), b))                    # malformed input -> nan
     assert np.isnan(safe_wasserstein([[0.1, 0.2], [0.3]], b))
-    big = np.sort(rng.random((600, 2)), axis=1)                               # beyond the engine's capacity
+    big = np.sort(rng.random((2100, 2)), axis=1)                              # beyond the engine's capacity (~4,000 points per pair)
     with pytest.raises(_lib.TdaError):
         safe_wasserstein(big, big)
 
