@@ -840,25 +840,64 @@ __global__ void __launch_bounds__(256) classify_bits_kernel(Params p) {
     extern __shared__ __align__(16) uint32_t cb_raw[];
     constexpr int NV = 32 * NWORDS;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    uint32_t* adj = cb_raw + (size_t)wib * (NV * NWORDS + NV);   // [NV][NWORDS]
+    constexpr int kPerWarp = NV * NWORDS + NV + NV / 2;            // words: bit rows, vertex lists, comp + eld bytes
+    uint32_t* adj = cb_raw + (size_t)wib * kPerWarp;               // [NV][NWORDS]
     uint32_t* touched = adj + NV * NWORDS;                         // [NV]
+    uint8_t* comp = reinterpret_cast<uint8_t*>(touched + NV);      // [NV] Kruskal: component of a vertex
+    uint8_t* eld = comp + NV;                                      // [NV] eldest vertex of a component
     const uint32_t lt = (1u << lane) - 1u;
     for (int c = blockIdx.x * wpb + wib; c < p.C; c += gridDim.x * wpb) {
-        const int n = cloud_n(p, p.c0 + c);
+        const int b = p.c0 + c;
+        const int n = cloud_n(p, b);
         const int m = n >= 2 ? p.m[c] : 0;
         uint32_t* Pc = p.P + (size_t)c * p.Emax;
         uint16_t* dvc = p.defv + (size_t)c * p.Emax;
+        const float* Db = p.D + (size_t)b * p.strideB;
         for (int q = lane; q < NV * NWORDS + NV; q += 32) adj[q] = 0;
+        for (int v = lane; v < NV; v += 32) { comp[v] = (uint8_t)v; eld[v] = (uint8_t)v; }
         __syncwarp();
+        int ncomp = n, n0 = 0;   // K3 (Kruskal, H0 pairs by the elder rule) rides on the same walk
         int births = 0;
         uint32_t prev_tie = 0;   // "rank c0 - 1 has the same length as rank c0"
         uint32_t qn = lane < m ? __ldg(Pc + lane) : 0u;
         for (int c0 = 0; c0 < m; c0 += 32) {
             const int r = c0 + lane;
             const bool act = r < m;
-            const uint32_t q = qn;
+            uint32_t q = qn;
             qn = r + 32 < m ? __ldg(Pc + r + 32) : 0u;   // (the flags this kernel sets are not read back)
             const int i = p_i(q), j = p_j(q);
+            // ---- merging edges of this step, in rank order
+            if (ncomp > 1) {
+                uint32_t bal = __ballot_sync(kFull, act && comp[i] != comp[j]);
+                uint32_t mst = 0;
+                while (bal && ncomp > 1) {
+                    const int src = __ffs(bal) - 1;
+                    bal &= bal - 1;
+                    const uint32_t qs = __shfl_sync(kFull, q, src);
+                    const int is = p_i(qs), js = p_j(qs);
+                    const int ci = comp[is], cj = comp[js];
+                    if (ci == cj) continue;
+                    const int ei = eld[ci], ej = eld[cj];
+                    const float d = __ldg(Db + (size_t)js * p.ld + is) + 0.0f;
+                    if (d != 0.0f) {
+                        if (lane == 0 && n0 < p.cap0) {
+                            const size_t o = ((size_t)b * p.cap0 + n0) * 2;
+                            p.bd0[o] = 0.0f;
+                            p.bd0[o + 1] = d;
+                            if (p.pr0) { p.pr0[o] = min(ei, ej); p.pr0[o + 1] = c2(is) + js; }
+                        }
+                        ++n0;
+                    }
+                    __syncwarp();
+                    for (int v = lane; v < n; v += 32)
+                        if (comp[v] == ci) comp[v] = (uint8_t)cj;
+                    if (lane == 0) eld[cj] = (uint8_t)max(ei, ej);
+                    __syncwarp();
+                    mst |= 1u << src;
+                    --ncomp;
+                }
+                if ((mst >> lane) & 1u) { q |= kMst; Pc[r] = q; }
+            }
             const uint32_t tn = __ballot_sync(kFull, act && (q & kTieNext));
             const bool tied = ((tn >> lane) & 1u) || (lane ? ((tn >> (lane - 1)) & 1u) : prev_tie);
             prev_tie = tn >> 31;
@@ -910,6 +949,25 @@ __global__ void __launch_bounds__(256) classify_bits_kernel(Params p) {
         }
         births = __reduce_add_sync(kFull, births);
         if (lane == 0 && births) atomicAdd(p.nbirth + c, births);
+        // ---- H0 essential classes: eldest vertex of every surviving component, ascending
+        __syncwarp();
+        for (int v0 = 0; v0 < n; v0 += 32) {
+            const int v = v0 + lane;
+            const bool is = v < n && eld[comp[v]] == v;
+            const uint32_t bal = __ballot_sync(kFull, is);
+            if (is) {
+                const int pos = n0 + __popc(bal & lt);
+                if (pos < p.cap0) {
+                    const size_t o = ((size_t)b * p.cap0 + pos) * 2;
+                    p.bd0[o] = 0.0f;
+                    p.bd0[o + 1] = __int_as_float(0x7F800000);
+                    if (p.pr0) { p.pr0[o] = v; p.pr0[o + 1] = -1; }
+                }
+            }
+            n0 += __popc(bal);
+        }
+        if (lane == 0) p.counts[2 * b] = n0;
+        __syncwarp();
     }
 }
 
@@ -1767,9 +1825,10 @@ extern "C" int tda_rips_h01_large(const float* D, const int* npts, int B, int N,
         }
         {
             ProfScope prof("rips_large_kruskal", st);
-            if (N <= 256) kruskal_kernel<256><<<C, 256, 0, st>>>(p);
-            else kruskal_kernel<1024><<<C, 1024, 0, st>>>(p);
-            count_launch();
+            if (N > 256) {   // (up to 256 points Kruskal rides on the classification's walk of the edge list)
+                kruskal_kernel<1024><<<C, 1024, 0, st>>>(p);
+                count_launch();
+            }
             if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
         }
         {
@@ -1780,16 +1839,14 @@ extern "C" int tda_rips_h01_large(const float* D, const int* npts, int B, int N,
                 classify_kernel<uint32_t, false><<<(unsigned)blocks, 256, 0, st>>>(p);
                 count_launch();
             } else {
-                const int nwords = N <= 128 ? 4 : 8;
-                const size_t smem = (size_t)8 * (32 * nwords * nwords + 32 * nwords) * 4;
-                int g = (C + 7) / 8;
-                const int gmax = kSms * (N <= 128 ? 8 : 3);
+                // a warp per cloud; 9.7 KB of shared memory per warp at 129-256 points: two-warp CTAs, 11 per SM
+                const int nwords = N <= 128 ? 4 : 8, wpb = N <= 128 ? 8 : 2;
+                const size_t smem = (size_t)wpb * (32 * nwords * nwords + 32 * nwords + 16 * nwords) * 4;
+                int g = (C + wpb - 1) / wpb;
+                const int gmax = kSms * (N <= 128 ? 8 : 11);
                 if (g > gmax) g = gmax;
-                if (N <= 128) classify_bits_kernel<4><<<g, 256, smem, st>>>(p);
-                else {
-                    cudaFuncSetAttribute(classify_bits_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    classify_bits_kernel<8><<<g, 256, smem, st>>>(p);
-                }
+                if (N <= 128) classify_bits_kernel<4><<<g, 32 * wpb, smem, st>>>(p);
+                else classify_bits_kernel<8><<<g, 32 * wpb, smem, st>>>(p);
                 count_launch();
                 if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
                 ProfScope prof2("rips_large_classify_tied", st);
