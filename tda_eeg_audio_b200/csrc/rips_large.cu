@@ -758,7 +758,14 @@ __global__ void __launch_bounds__(256) classify_kernel(Params p) {
         const uint32_t* keys = p.skey + (size_t)c * p.Emax;
         const int i = p_i(q), j = p_j(q);
         const bool tied = (q & kTieNext) || (r > 0 && (Pc[r - 1] & kTieNext));
-        if (ONLY_TIED && !tied) continue;
+        if (ONLY_TIED) {
+            // (16-bit ranks: classify_bits_kernel has taken every run that lies inside one of its 32-rank steps)
+            if (!tied) continue;
+            int r0 = r, r1 = r + 1;
+            while (r0 > 0 && (Pc[r0 - 1] & kTieNext)) --r0;
+            while (Pc[r1 - 1] & kTieNext) ++r1;
+            if ((r0 >> 5) == ((r1 - 1) >> 5)) continue;
+        }
         const uint32_t k32r = tied ? keys[r] : 0u;
         const uint4* Ti = reinterpret_cast<const uint4*>(Tc + (size_t)i * p.ldT);
         const uint4* Tj = reinterpret_cast<const uint4*>(Tc + (size_t)j * p.ldT);
@@ -898,13 +905,22 @@ __global__ void __launch_bounds__(256) classify_bits_kernel(Params p) {
                 }
                 if ((mst >> lane) & 1u) { q |= kMst; Pc[r] = q; }
             }
+            // ---- tie runs inside the step.  The first cofacet of a run member is decided with the whole run present
+            //      (lanes below `bl`, the end of its run), and it is an apparent pair only if both other edges of
+            //      that triangle are strictly earlier (lanes below its own).  A run that reaches into the previous
+            //      or the next step is left to classify_kernel<ONLY_TIED>.
             const uint32_t tn = __ballot_sync(kFull, act && (q & kTieNext));
-            const bool tied = ((tn >> lane) & 1u) || (lane ? ((tn >> (lane - 1)) & 1u) : prev_tie);
+            const uint32_t nx = ~(tn >> lane);
+            const int bl = lane + (nx ? __ffs(nx) : 33);                                   // (exclusive); > 32: into the next step
+            const int nbelow = lane ? __clz(~((tn & lt) << (32 - lane))) : 0;              // run members below this lane
+            const bool cross = bl > 32 || (nbelow == lane && prev_tie);
             prev_tie = tn >> 31;
+            const uint32_t pm = (bl >= 32 ? kFull : ((1u << bl) - 1u)) & ~(1u << lane);     // present by the end of the run
             if (act) { atomicOr(touched + i, 1u << lane); atomicOr(touched + j, 1u << lane); }
             __syncwarp();
-            const bool want = act && !(q & kMst) && !tied;
+            const bool want = act && !(q & kMst) && !cross;
             int vc = -1;
+            bool strict = true;   // both other edges of the triangle (i, j, vc) are strictly earlier than this edge
             uint32_t tl = 0;
             if (want) {
                 const uint4* ai = reinterpret_cast<const uint4*>(adj + i * NWORDS);
@@ -917,28 +933,31 @@ __global__ void __launch_bounds__(256) classify_bits_kernel(Params p) {
                     for (int k = 3; k >= 0; --k)
                         if (vc < 0 && cm[k]) vc = 32 * (4 * w4 + k) + 31 - __clz(cm[k]);
                 }
-                tl = (touched[i] | touched[j]) & lt;
+                tl = (touched[i] | touched[j]) & pm;
             }
             while (__any_sync(kFull, tl != 0)) {
                 const int l2 = tl ? __ffs(tl) - 1 : lane;
                 const uint32_t q2 = __shfl_sync(kFull, q, l2);
                 if (tl) {
                     tl &= tl - 1;
-                    const int a = p_i(q2), b = p_j(q2);
+                    const int a = p_i(q2), b2 = p_j(q2);
                     const bool at_a = (a == i) || (a == j);
-                    const int s = at_a ? a : b, v = at_a ? b : a;   // shared vertex, candidate apex
-                    const int o = (s == i) ? j : i;                 // the end point of this edge that is not shared
+                    const int s = at_a ? a : b2, v = at_a ? b2 : a;  // shared vertex, candidate apex
+                    const int o = (s == i) ? j : i;                  // the end point of this edge that is not shared
                     if (v > vc) {
-                        bool ok = (adj[o * NWORDS + (v >> 5)] >> (v & 31)) & 1u;
-                        if (!ok) ok = (touched[o] & touched[v] & lt) != 0;   // edge (o, v) earlier in this step
-                        if (ok) vc = v;
+                        const bool pre = (adj[o * NWORDS + (v >> 5)] >> (v & 31)) & 1u;
+                        const uint32_t l3 = touched[o] & touched[v] & pm;   // edge (o, v) in this step, inside the run's reach
+                        if (pre || l3) {
+                            vc = v;
+                            strict = l2 < lane && (pre || (l3 & lt) != 0);
+                        }
                     }
                 }
             }
             __syncwarp();
             if (act) { touched[i] = 0; touched[j] = 0; }
             if (want) {
-                if (vc < 0) { Pc[r] = q | kBirth; ++births; }
+                if (vc < 0 || !strict) { Pc[r] = q | kBirth; ++births; }
                 else dvc[r] = (uint16_t)vc;
             }
             if (act) {
