@@ -119,6 +119,8 @@ struct Params {
     int* queue;         // next position of the current sweep launch
     const int* order;   // position -> cloud, heaviest first (nullptr: positions are clouds)
     int* nbirth;        // [C] number of H1 births of every cloud (classify), the weight behind `order`
+    uint2* left;           // (cloud, rank) of the tie-run members classify_bits_kernel leaves to the rank-row walk
+    int* n_left;
     // big clouds: adjacency bit rows at six early ranks (classification of the early edges)
     const uint32_t* lev;   // [C][kLevels][N][kLevWords]; nullptr: none
     const int* levR;       // [C][2 kLevels]: the level ranks, then the same extended to the end of their tie runs
@@ -745,10 +747,13 @@ template <typename TT, bool ONLY_TIED>
 __global__ void __launch_bounds__(256) classify_kernel(Params p) {
     constexpr int VPL = 16 / (int)sizeof(TT);   // ranks per 16-byte load
     constexpr uint32_t kAbsent = RankOf<TT>::kAbsent;
-    const uint32_t total = (uint32_t)(p.Emax * p.C), emax = (uint32_t)p.Emax;   // (< 2^31: make_plan)
+    // ONLY_TIED: the (cloud, rank) items classify_bits_kernel left over, from its list; else every edge of the chunk
+    const uint32_t emax = (uint32_t)p.Emax;
+    const uint32_t total = ONLY_TIED ? (uint32_t)*p.n_left : (uint32_t)(p.Emax * p.C);   // (< 2^31: make_plan)
     for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
-        const int c = (int)(w / emax);
-        const int r = (int)(w - (uint32_t)c * emax);
+        int c, r;
+        if (ONLY_TIED) { const uint2 it = p.left[w]; c = (int)it.x; r = (int)it.y; }
+        else { c = (int)(w / emax); r = (int)(w - (uint32_t)c * emax); }
         if (r >= p.m[c]) continue;
         uint32_t* Pc = p.P + (size_t)c * p.Emax;
         const uint32_t q = Pc[r];
@@ -758,14 +763,7 @@ __global__ void __launch_bounds__(256) classify_kernel(Params p) {
         const uint32_t* keys = p.skey + (size_t)c * p.Emax;
         const int i = p_i(q), j = p_j(q);
         const bool tied = (q & kTieNext) || (r > 0 && (Pc[r - 1] & kTieNext));
-        if (ONLY_TIED) {
-            // (16-bit ranks: classify_bits_kernel has taken every run that lies inside one of its 32-rank steps)
-            if (!tied) continue;
-            int r0 = r, r1 = r + 1;
-            while (r0 > 0 && (Pc[r0 - 1] & kTieNext)) --r0;
-            while (Pc[r1 - 1] & kTieNext) ++r1;
-            if ((r0 >> 5) == ((r1 - 1) >> 5)) continue;
-        }
+
         const uint32_t k32r = tied ? keys[r] : 0u;
         const uint4* Ti = reinterpret_cast<const uint4*>(Tc + (size_t)i * p.ldT);
         const uint4* Tj = reinterpret_cast<const uint4*>(Tc + (size_t)j * p.ldT);
@@ -919,6 +917,16 @@ __global__ void __launch_bounds__(256) classify_bits_kernel(Params p) {
             if (act) { atomicOr(touched + i, 1u << lane); atomicOr(touched + j, 1u << lane); }
             __syncwarp();
             const bool want = act && !(q & kMst) && !cross;
+            {   // members of a run that crosses a step boundary go on the list of the rank-row walk
+                const bool push = act && !(q & kMst) && cross;
+                const uint32_t pb = __ballot_sync(kFull, push);
+                if (pb) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(p.n_left, __popc(pb));
+                    base = __shfl_sync(kFull, base, 0);
+                    if (push) p.left[base + __popc(pb & lt)] = make_uint2((uint32_t)c, (uint32_t)r);
+                }
+            }
             int vc = -1;
             bool strict = true;   // both other edges of the triangle (i, j, vc) are strictly earlier than this edge
             uint32_t tl = 0;
@@ -1798,6 +1806,8 @@ extern "C" int tda_rips_h01_large(const float* D, const int* npts, int B, int N,
     p.rec = (uint32_t*)(w8 + pl.rec); p.sglob = (uint32_t*)(w8 + pl.sglob);
     p.worklist = nullptr; p.n_work = nullptr; p.overflow_list = nullptr; p.n_overflow = nullptr;
     p.queue = nullptr; p.order = nullptr; p.nbirth = (int*)(w8 + pl.nbirth);
+    p.left = (uint2*)(w8 + pl.sortbuf);   // (the sort arrays are free once the rank kernel is done)
+    p.n_left = (int*)(w8 + pl.counters) + 2;
     p.lev = N > 256 ? (const uint32_t*)(w8 + pl.lev) : nullptr;
     p.levR = N > 256 ? (const int*)(w8 + pl.levR) : nullptr;
     cudaError_t e;
@@ -1869,7 +1879,7 @@ extern "C" int tda_rips_h01_large(const float* D, const int* npts, int B, int N,
                 count_launch();
                 if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
                 ProfScope prof2("rips_large_classify_tied", st);
-                classify_kernel<uint16_t, true><<<(unsigned)blocks, 256, 0, st>>>(p);   // members of tie runs
+                classify_kernel<uint16_t, true><<<kSms * 4, 256, 0, st>>>(p);   // tie runs across a step boundary
                 count_launch();
             }
             if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
