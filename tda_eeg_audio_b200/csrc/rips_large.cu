@@ -1473,6 +1473,22 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
                 if constexpr (NTH == 32) {   // the chunk is the warp's registers: shuffles, no shared memory, no barrier
                     fpe = __shfl_sync(kFull, pe, first - rbase);
                     fdv = __shfl_sync(kFull, dv, first - rbase);
+                    if constexpr (sizeof(TT) == 2) {
+                        // the rank and index rows of the edge that is likely to be visited next (the next flagged rank
+                        // of the chunk) start their way from DRAM now: the tables of the resident clouds are ~1 GB,
+                        // every visited edge otherwise waits a full DRAM round trip for its four rows
+                        const int second = __reduce_min_sync(kFull, (flag && rr > first) ? rr : 0x7FFFFFFF);
+                        if (second != 0x7FFFFFFF) {
+                            const uint32_t pe2 = __shfl_sync(kFull, pe, second - rbase);
+                            if (lane < 16) {
+                                const int v2 = (lane & 4) ? p_j(pe2) : p_i(pe2);
+                                const char* row = (lane & 8) ? reinterpret_cast<const char*>(Q + (size_t)v2 * ldT)
+                                                             : reinterpret_cast<const char*>(T + (size_t)v2 * ldT);
+                                const int off = (lane & 3) * 128;
+                                if (off < ldT * 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off));
+                            }
+                        }
+                    }
                     const uint32_t pv = __shfl_sync(kFull, pe, (first - rbase + 31) & 31);
                     if (first > rbase) ppe = pv;
                     else if (first > 0) ppe = __ldg(P + first - 1);
