@@ -1459,6 +1459,15 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
                 const int rn = rr + NTH;
                 pe_nx = kMst; dv_nx = 0;
                 if (rn < m) { pe_nx = __ldg(P + rn); dv_nx = defv[rn]; }
+                if constexpr (NTH == 32) {
+                    // a chunk without a visited edge is over in a few instructions: the edge words further ahead
+                    // are requested from DRAM eight chunks early (one 128-byte line of P, half a line of defv)
+                    const int ra = rbase + 8 * NTH;
+                    if (tid == 0 && ra < m) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(P + ra));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(defv + ra));
+                    }
+                }
             }
             const int rend = min(rbase + NTH, m);
             int done = rbase;
