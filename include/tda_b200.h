@@ -85,8 +85,9 @@ int tda_rips_h01_batched(const float* D, int B, int N, int ld, long long strideB
  * stress, BASELINE.json configs[4]; the 97-248 point Takens clouds of the audio path; any batch
  * above the 64-point engine).  Same outputs and conventions as tda_rips_h01_batched; differences:
  * `npts` (may be NULL) gives the point count of every item (<= N, the leading npts x npts block of
- * the ld x ld matrix is used), and the H0 output has an explicit row capacity cap0 (bd0 (B, cap0, 2)).  Grid-wide cooperative phases over a chunk of
- * clouds (edge keys, one device-wide radix sort, rank matrices, Kruskal, first-cofacet /
+ * the ld x ld matrix is used), and the H0 output has an explicit row capacity cap0 (bd0 (B, cap0, 2)).
+ * Phases over a chunk of clouds (edge keys + stable radix sort + rank matrices: per cloud in shared
+ * memory up to 256 points, grid-wide over L2-resident groups of clouds above; Kruskal; first-cofacet /
  * apparent-pair classification of every edge) followed by one CTA per cloud for the serial part
  * (cocycle sweep over the edges a live class can see).  The chunk size follows from `ws_bytes`;
  * tda_rips_h01_large_workspace_bytes returns a size that holds min(B, what fits 48 GB) clouds.

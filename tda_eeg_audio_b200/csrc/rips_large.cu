@@ -11,23 +11,25 @@
 // Here (oracle/pcoh_large_model.cpp is the executable statement of the algorithm, validated on
 // CPU) the work is split into grid-wide data-parallel phases over ALL clouds of a chunk and a
 // short serial sweep per cloud:
-//   K1 rank      one CTA per cloud: the order-preserving integer image of every f32 edge length, laid out in
-//                descending edge index, then a stable LSD radix sort of (key, (i, j)) -- 8-bit digits, a
-//                segment of the array and a row of digit counters per warp, __match_any_sync ranks inside a
-//                chunk of 32, passes over bytes equal in all keys skipped -- whose stability yields Ripser's
-//                tie-break (equal length => larger index first); sorted position r -> P[r] = (i, j, tie
-//                flag), rank matrix T[i][j] = r (16-bit ranks up to 256 points: half the bytes of the table
-//                every later phase reads by rows)
-//   K3 kruskal   one CTA per cloud: MST flags + the H0 pairs (elder rule for the vertex)
-//   K4 classify  one thread per edge, cooperative over the whole grid: the first cofacet of every
-//                non-MST edge (largest apex v with T[i][v], T[j][v] inside the edge's tie run or
-//                before it).  If that triangle has the edge as its youngest edge the two form an
-//                apparent zero-persistence pair (defv = v) — >99 % of all columns end here —
-//                otherwise the edge gives BIRTH to an H1 class.
+//   K1 rank      the order-preserving integer image of every f32 edge length, laid out in descending edge index,
+//                then a stable LSD radix sort of (key, (i, j)) -- 8-bit digits, lanes with the same digit found by
+//                ballots -- whose stability yields Ripser's tie-break (equal length => larger index first); sorted
+//                position r -> P[r] = (i, j, tie flag), rank matrix T[i][j] = r.  Up to 256 points (the audio
+//                path): one CTA per cloud, the whole array in shared memory, in-place passes through registers,
+//                16-bit ranks.  Above: a grid-wide sort of a group of clouds at a time, as many as keep their
+//                sort arrays and rank matrices in L2 (keys / per-tile histograms / staged stable scatter / finish).
+//   K3 kruskal   MST flags + the H0 pairs (elder rule for the vertex): up to 256 points inside K4's walk of the
+//                edge list, above one CTA per cloud
+//   K4 classify  the first cofacet of every non-MST edge (largest apex v with T[i][v], T[j][v] inside the edge's
+//                tie run or before it).  If that triangle has the edge as its youngest edge the two form an
+//                apparent zero-persistence pair (defv = v) -- >99 % of all columns end here -- otherwise the edge
+//                gives BIRTH to an H1 class.  Up to 256 points: one warp per cloud, 32 ranks per step, the
+//                adjacency of the earlier ranks as bit rows in shared memory.  Above: one thread per edge over the
+//                whole grid walking two rank rows, the early edges through adjacency bit rows at six early ranks.
 //   K5 sweep     one CTA per cloud, persistent cohomology by cocycle annotation restricted to the
 //                edges a live cocycle can see: S[v] = OR of the cocycle masks over the edges at v;
 //                an edge with (S[i] | S[j]) & live == 0 has PHI = 0 and coboundary 0 on all of
-//                its triangles and is skipped by a block-wide scan of 1,024 ranks per step.  The
+//                its triangles and is skipped by a scan of the chunk's ranks.  The
 //                visited tie runs (a single edge is a run of one) are handled exactly:
 //                  A. rank order: births take a slot, visible apparent edges get
 //                     PHI[e] := PHI[i,defv] ^ PHI[j,defv]   (non-zero values live in a compact
