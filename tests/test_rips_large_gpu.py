@@ -81,8 +81,8 @@ def test_large_uniform_and_ties(cuda):
     _compare(D, 2.5)
 
 
-def test_large_degenerate_ragged_nan(cuda):
-    n = 300
+@pytest.mark.parametrize("n", [100, 200, 300])   # the three size classes of the sort / classification kernels
+def test_large_degenerate_ragged_nan(cuda, n):
     D = np.zeros((5, n, n), np.float32)
     D[1] = 1.0
     D[2] = takens_like(np.random.default_rng(0), 1, n)[0]
@@ -92,8 +92,8 @@ def test_large_degenerate_ragged_nan(cuda):
     for b in range(5):
         np.fill_diagonal(D[b], 0)
     _compare(D, 2.0, cap1=2048)
-    _compare(D, 2.0, npts=[1, 2, 60, 300, 3], cap1=2048)
-    D[4, 3, 200] = np.nan
+    _compare(D, 2.0, npts=[1, 2, 60, n, 3], cap1=2048)
+    D[4, 3, n - 7] = np.nan
     D[4, 10, 11] = np.nan
     g = _compare(D, 2.0, cap1=2048)
     assert g["status"][4] & 2 and not (g["status"][:4] & 2).any()
