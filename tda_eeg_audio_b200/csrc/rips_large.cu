@@ -1845,7 +1845,6 @@ extern "C" int tda_rips_h01_large(const float* D, const int* npts, int B, int N,
         {
             // keys + per-CTA radix sort + rank matrix in one kernel (fills T, Q, m, nanflag of the chunk)
             ProfScope prof("rips_large_rank", st);
-            const int grid = C < kSms ? C : kSms;
             if (N <= 128) e = launch_rank_small<512, 16, 3>(p, st);          // E <= 8,128: three clouds per SM
             else if (N <= 170) e = launch_rank_small<512, 32, 2>(p, st);     // E <= 14,365, T <= 64 KB: two
             else if (N <= 256) e = launch_rank_small<1024, 32, 1>(p, st);    // E <= 32,640: 209 KB, one
