@@ -138,3 +138,33 @@ def test_full_size_properties_without_the_oracle(cuda):
     assert cnt[0, 1] > 100 and (h1[:, 0] < h1[:, 1]).all()
     lengths = np.unique(D[np.triu_indices(n, 1)])
     assert np.isin(h1[:, 0], lengths).all() and np.isin(h1[np.isfinite(h1[:, 1]), 1], lengths).all()
+
+
+@pytest.mark.parametrize("n", [150, 300])
+def test_large_batch_in_several_chunks(cuda, n):
+    """A workspace that holds only a few clouds: the batch is worked off chunk by chunk (every per-chunk
+    array, counter and list is re-used) and must give the very bits of the one-chunk run."""
+    import torch
+    from tda_eeg_audio_b200 import _lib, rips_h01_batched
+    lib = _lib.load()
+    B, cap1 = 11, 1024
+    D = torch.from_numpy(takens_like(np.random.default_rng(40 + n), B, n)).cuda()
+    D[::3] = torch.round(D[::3] * 128) / 128          # tie runs in some of the clouds
+    ref = rips_h01_batched(D, thresh=2.0, cap1=cap1, want_pairs=True, engine="large")
+    torch.cuda.synchronize()
+    wsb = int(lib.tda_rips_h01_large_workspace_bytes(3, n))
+    assert wsb < int(lib.tda_rips_h01_large_workspace_bytes(B, n))
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    bd0 = torch.zeros((B, n, 2), dtype=torch.float32, device="cuda"); pr0 = torch.zeros((B, n, 2), dtype=torch.int64, device="cuda")
+    bd1 = torch.zeros((B, cap1, 2), dtype=torch.float32, device="cuda"); pr1 = torch.zeros((B, cap1, 2), dtype=torch.int64, device="cuda")
+    counts = torch.zeros((B, 2), dtype=torch.int32, device="cuda"); status = torch.zeros(B, dtype=torch.int32, device="cuda")
+    rc = lib.tda_rips_h01_large(D.data_ptr(), None, B, n, D.stride(1), D.stride(0), 2.0, bd0.data_ptr(), pr0.data_ptr(), n,
+                                bd1.data_ptr(), pr1.data_ptr(), cap1, counts.data_ptr(), status.data_ptr(),
+                                ws.data_ptr(), wsb, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert rc == 0
+    assert torch.equal(counts, ref["counts"]) and not bool(status.any())
+    for b in range(B):
+        n0, n1 = (int(x) for x in counts[b])
+        assert torch.equal(bd0[b, :n0], ref["bd0"][b, :n0]) and torch.equal(pr0[b, :n0], ref["pr0"][b, :n0])
+        assert torch.equal(bd1[b, :n1], ref["bd1"][b, :n1]) and torch.equal(pr1[b, :n1], ref["pr1"][b, :n1])
