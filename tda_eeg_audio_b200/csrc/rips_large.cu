@@ -443,26 +443,29 @@ __global__ void __launch_bounds__(256) levels_big_kernel(Params p, SortGroup sg,
 // payloads follow in a second round through the saved positions, so that never more than EPT + EPT / 2 data
 // registers are live.  Nothing but D is read from and nothing but P, the sorted keys, T and Q is written to
 // global memory; T is assembled in the key array's space and leaves as 16-byte rows.
-constexpr int kCntStride = 258;   // u16 per counter row: 516 bytes, rows start in different banks
-template <int NTH, int EPT> struct RankSmall {
+// digits of a pass: 256 (8 bits), or -- NINE, where the shared memory allows -- 512 when only 27 key bits vary: three
+// passes of 9 bits instead of four of 8.  Counter rows of kDig + 2 u16: an odd number of words, rows start in different banks
+template <int NTH, int EPT, bool NINE> struct RankSmall {
     static constexpr int NW = NTH / 32;
     static constexpr int kCap = NTH * EPT;
+    static constexpr int kDigMax = NINE ? 512 : 256;
+    static constexpr int kCntStride = kDigMax + 2;
     static constexpr size_t kKeyBytes = (size_t)kCap * 4;
-    static constexpr size_t kSmem = kKeyBytes + (size_t)kCap * 2 + (size_t)NW * kCntStride * 2 + 256 * 4 + 256 * 4 + 4 * NW * 4 + 64;
+    static constexpr size_t kSmem = kKeyBytes + (size_t)kCap * 2 + (size_t)NW * kCntStride * 2 + kDigMax * 2 + kDigMax * 2 + 4 * NW * 4 + 64;
 };
 
-template <int NTH, int EPT, int MINB>
+template <int NTH, int EPT, int MINB, bool NINE>
 __global__ void __launch_bounds__(NTH, MINB) rank_small_kernel(Params p) {
-    using RS = RankSmall<NTH, EPT>;
+    using RS = RankSmall<NTH, EPT, NINE>;
     constexpr int NW = RS::NW;
-    constexpr int DPW = 256 / NW;   // digits scanned per warp
+    constexpr int kDigMax = RS::kDigMax, kCntStride = RS::kCntStride;
     extern __shared__ __align__(16) unsigned char rs_raw[];
     uint32_t* K = reinterpret_cast<uint32_t*>(rs_raw);                                  // [kCap] keys; later T
     uint16_t* Pp = reinterpret_cast<uint16_t*>(rs_raw + RS::kKeyBytes);                 // [kCap] i << 8 | j
     uint16_t* cnt = Pp + RS::kCap;                                                      // [NW][kCntStride]
-    uint32_t* tot = reinterpret_cast<uint32_t*>(cnt + NW * kCntStride);                 // [256] elements per digit
-    uint32_t* dbase = tot + 256;                                                        // [256] first position per digit
-    uint32_t* red = dbase + 256;                                                        // [4 NW]
+    uint16_t* tot = cnt + NW * kCntStride;                                              // [kDigMax] elements per digit
+    uint16_t* dbase = tot + kDigMax;                                                    // [kDigMax] first position per digit
+    uint32_t* red = reinterpret_cast<uint32_t*>(dbase + kDigMax);                       // [4 NW]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = (1u << lane) - 1u;
     for (int c = blockIdx.x; c < p.C; c += gridDim.x) {
@@ -500,9 +503,14 @@ __global__ void __launch_bounds__(NTH, MINB) rank_small_kernel(Params p) {
         const int nch = (E + NTH - 1) / NTH;          // chunks of 32 elements per warp
         const int seg0 = warp * nch * 32;             // first element of this warp's segment
         uint32_t* row32 = reinterpret_cast<uint32_t*>(cnt + warp * kCntStride);
-        for (int pass = 0; pass < 4; ++pass) {
-            const int sh = 8 * pass;
-            if (!((varying >> sh) & 255u)) continue;
+        // distances of a normalised cloud lie in [2^-15, 2): the five top bits of every key are the same and the 27
+        // others sort in THREE passes of 9-bit digits (512 counters per warp); otherwise four passes of 8
+        const int db = (NINE && !(varying >> 27)) ? 9 : 8;
+        const uint32_t dmask = (1u << db) - 1u;
+        const int ndig = 1 << db;
+        for (int pass = 0; pass * db < 32; ++pass) {
+            const int sh = db * pass;
+            if (!((varying >> sh) & dmask)) continue;
             {
                 uint32_t* c32 = reinterpret_cast<uint32_t*>(cnt);
                 for (int q = tid; q < NW * kCntStride / 2; q += NTH) c32[q] = 0;
@@ -516,15 +524,15 @@ __global__ void __launch_bounds__(NTH, MINB) rank_small_kernel(Params p) {
                 const bool act = t < nch && k < E;
                 kr[t] = act ? K[k] : 0u;
                 if (act) {
-                    const uint32_t dg = (kr[t] >> sh) & 255u;
+                    const uint32_t dg = (kr[t] >> sh) & dmask;
                     atomicAdd(row32 + (dg >> 1), 1u << (16 * (dg & 1u)));
                 }
             }
             __syncthreads();
             // ---- per digit: exclusive scan over the warps (lane = warp row), total per digit
-#pragma unroll
-            for (int dd = 0; dd < DPW; ++dd) {
-                const int d = warp * DPW + dd;
+            const int dpw = ndig / NW;   // digits scanned per warp
+            for (int dd = 0; dd < dpw; ++dd) {
+                const int d = warp * dpw + dd;
                 const uint32_t own = lane < NW ? cnt[lane * kCntStride + d] : 0u;
                 uint32_t incl = own;
 #pragma unroll
@@ -533,13 +541,14 @@ __global__ void __launch_bounds__(NTH, MINB) rank_small_kernel(Params p) {
                     if (lane >= o) incl += y;
                 }
                 if (lane < NW) cnt[lane * kCntStride + d] = (uint16_t)(incl - own);
-                if (lane == 31) tot[d] = incl;
+                if (lane == 31) tot[d] = (uint16_t)incl;
             }
             __syncthreads();
-            if (warp == 0) {   // first position of every digit: eight digits per lane
-                uint32_t v[8], run = 0;
+            if (warp == 0) {   // first position of every digit: 8 or 16 digits per lane
+                const int dpl = ndig >> 5;
+                uint32_t v[kDigMax / 32], run = 0;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) { v[q] = tot[8 * lane + q]; run += v[q]; }
+                for (int q = 0; q < kDigMax / 32; ++q) { v[q] = q < dpl ? tot[dpl * lane + q] : 0u; run += v[q]; }
                 uint32_t incl = run;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -548,7 +557,7 @@ __global__ void __launch_bounds__(NTH, MINB) rank_small_kernel(Params p) {
                 }
                 uint32_t base = incl - run;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) { dbase[8 * lane + q] = base; base += v[q]; }
+                for (int q = 0; q < kDigMax / 32; ++q) { if (q < dpl) dbase[dpl * lane + q] = (uint16_t)base; base += v[q]; }
             }
             __syncthreads();
             // ---- keys to their positions (stable: chunks in order, lanes ranked inside a chunk)
@@ -557,12 +566,12 @@ __global__ void __launch_bounds__(NTH, MINB) rank_small_kernel(Params p) {
             for (int t = 0; t < EPT; ++t) {
                 const int k = seg0 + 32 * t + lane;
                 const bool act = t < nch && k < E;
-                // lanes with the same digit: eight ballots (one per digit bit).  __match_any_sync takes a step per
-                // distinct value, ~30 of them among 32 random digits, and was half of this kernel's stall samples
-                const uint32_t dg = (kr[t] >> sh) & 255u;
+                // lanes with the same digit: a ballot per digit bit.  __match_any_sync takes a step per distinct
+                // value, ~30 of them among 32 random digits, and was half of this kernel's stall samples
+                const uint32_t dg = (kr[t] >> sh) & dmask;
                 uint32_t peers = __ballot_sync(kFull, act);
 #pragma unroll
-                for (int bt = 0; bt < 8; ++bt) {
+                for (int bt = 0; bt < 9; ++bt) {
                     const uint32_t bal = __ballot_sync(kFull, (dg >> bt) & 1u);
                     peers &= ((dg >> bt) & 1u) ? bal : ~bal;
                 }
@@ -1639,12 +1648,12 @@ __global__ void __launch_bounds__(NTH) sweep_kernel(Params p, int rezero_q) {
     }
 }
 
-template <int NTH, int EPT, int MINB> static cudaError_t launch_rank_small(const Params& p, cudaStream_t st) {
-    const size_t smem = RankSmall<NTH, EPT>::kSmem;
-    cudaError_t e = cudaFuncSetAttribute(rank_small_kernel<NTH, EPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int NTH, int EPT, int MINB, bool NINE> static cudaError_t launch_rank_small(const Params& p, cudaStream_t st) {
+    const size_t smem = RankSmall<NTH, EPT, NINE>::kSmem;
+    cudaError_t e = cudaFuncSetAttribute(rank_small_kernel<NTH, EPT, MINB, NINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = p.C < kSmCount * MINB ? p.C : kSmCount * MINB;
-    rank_small_kernel<NTH, EPT, MINB><<<grid, NTH, smem, st>>>(p);
+    rank_small_kernel<NTH, EPT, MINB, NINE><<<grid, NTH, smem, st>>>(p);
     return cudaSuccess;
 }
 
@@ -1845,9 +1854,9 @@ extern "C" int tda_rips_h01_large(const float* D, const int* npts, int B, int N,
         {
             // keys + per-CTA radix sort + rank matrix in one kernel (fills T, Q, m, nanflag of the chunk)
             ProfScope prof("rips_large_rank", st);
-            if (N <= 128) e = launch_rank_small<512, 16, 3>(p, st);          // E <= 8,128: three clouds per SM
-            else if (N <= 170) e = launch_rank_small<512, 32, 2>(p, st);     // E <= 14,365, T <= 64 KB: two
-            else if (N <= 256) e = launch_rank_small<1024, 32, 1>(p, st);    // E <= 32,640: 209 KB, one
+            if (N <= 128) e = launch_rank_small<512, 16, 3, true>(p, st);    // E <= 8,128: three clouds per SM
+            else if (N <= 170) e = launch_rank_small<512, 32, 2, false>(p, st);   // E <= 14,365, T <= 64 KB: two (8-bit digits: the 9-bit counters would cost the second CTA)
+            else if (N <= 256) e = launch_rank_small<1024, 32, 1, true>(p, st);   // E <= 32,640: 227 KB, one
             else {
                 // the grid-wide sort, a group of clouds at a time (their arrays stay in L2 from the keys to the rank matrix)
                 if ((e = cudaMemsetAsync(w8 + pl.m, 0, pl.list - pl.m, st)) != cudaSuccess) return (int)e;   // m, nanflag
