@@ -1102,7 +1102,8 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
     // warp 0 only: birth / definition of one edge.  0 = no live cocycle sees it, 1 = visited,
     // 2 = birth without a free slot (nothing changed; the CTA scrubs and calls again).
     // Leaves the edge's value in peval[].
-    __device__ int edge_a(int pr, uint32_t pe, int dv) {
+    // REC: the edge goes on the list of visited edges of a tie run (a single edge needs no list)
+    template <bool REC = true> __device__ int edge_a(int pr, uint32_t pe, int dv) {
         const int x = p_i(pe), y = p_j(pe);
         uint32_t val = 0;
         if (pe & kBirth) {
@@ -1130,8 +1131,10 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
         if (__ballot_sync(kFull, val != 0)) {
             if (!append(pr, x, y, val)) return 0;
         }
-        if (lane == 0) { act[ctl[1]] = (uint32_t)pr; ctl[1] = ctl[1] + 1; }
-        __syncwarp();
+        if constexpr (REC) {
+            if (lane == 0) { act[ctl[1]] = (uint32_t)pr; ctl[1] = ctl[1] + 1; }
+            __syncwarp();
+        }
         return 1;
     }
     // warp 0 only.  Returns the rank to resume from after a scrub, or r1 when done.
@@ -1397,9 +1400,8 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
             }
         }
         if (warp == 0) {
-            if (lane == 0) ctl[1] = 0;
-            __syncwarp();
-            const int code = edge_a(pr, pe, dv);
+            if (lane == 0) ctl[1] = 1;   // one visited edge (the death loop takes it from its arguments)
+            const int code = edge_a<false>(pr, pe, dv);
             if (lane == 0) ctl[6] = code;
         }
         bar();
