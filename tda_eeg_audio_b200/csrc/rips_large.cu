@@ -1367,9 +1367,10 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
         // 256 points: NTH * 4 covers the padded row), so each of the four rows is one 8-byte load per thread;
         // the padding of a row is "absent" in T and 0 in Q (rank_small_kernel), no bounds test needed
         constexpr bool kVec = sizeof(TT) == 2 && (APT == 4 || APT == 8);
+        constexpr int NPK = kVec ? APT / 2 : 1;
+        uint32_t a[NPK], b[NPK], qx[NPK], qy[NPK];   // kVec: two 16-bit ranks / indices per word, kept packed
         if constexpr (kVec) {
             // APT consecutive apexes per thread: each of the four rows is one 8- or 16-byte load per thread
-            uint32_t a[APT / 2], b[APT / 2], qx[APT / 2], qy[APT / 2];
 #pragma unroll
             for (int k = 0; k < APT / 2; ++k) { a[k] = 0xFFFFFFFFu; b[k] = 0xFFFFFFFFu; qx[k] = 0u; qy[k] = 0u; }
             if (APT * tid < ldT) {
@@ -1384,12 +1385,6 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
                     a[0] = ta4.x; a[1] = ta4.y; a[2] = ta4.z; a[3] = ta4.w; b[0] = tb4.x; b[1] = tb4.y; b[2] = tb4.z; b[3] = tb4.w;
                     qx[0] = qx4.x; qx[1] = qx4.y; qx[2] = qx4.z; qx[3] = qx4.w; qy[0] = qy4.x; qy[1] = qy4.y; qy[2] = qy4.z; qy[3] = qy4.w;
                 }
-            }
-#pragma unroll
-            for (int h = 0; h < APT; ++h) {
-                const int sh = 16 * (h & 1);
-                ta[h] = (a[h >> 1] >> sh) & 0xFFFFu; tb[h] = (b[h >> 1] >> sh) & 0xFFFFu;
-                qa[h] = (int)((qx[h >> 1] >> sh) & 0xFFFFu); qb[h] = (int)((qy[h >> 1] >> sh) & 0xFFFFu);
             }
         } else {
 #pragma unroll
@@ -1413,13 +1408,34 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
 #pragma unroll
         for (int w = 0; w < W; ++w) { pv[w] = peval[w]; pany |= pv[w]; }
         uint32_t best = 0;
+        if constexpr (kVec) {
+            // two apexes per word: "both other edges earlier" and "an index entry on one of them" as packed
+            // 16-bit compares (absent = 0xFFFF is never below a rank)
+            const uint32_t pr2 = (uint32_t)pr * 0x10001u;
 #pragma unroll
-        for (int h = 0; h < APT; ++h) {
-            if (ta[h] < (uint32_t)pr && tb[h] < (uint32_t)pr) {
-                if (qa[h] | qb[h]) {
+            for (int k = 0; k < NPK; ++k) {
+                const uint32_t vm = __vcmpltu2(__vmaxu2(a[k], b[k]), pr2);
+                const uint32_t nzm = __vcmpne2(qx[k] | qy[k], 0u);
+                if (pany && (vm & ~nzm)) best = 1u;   // the other edges carry 0: the mask is the edge's own value
+                const uint32_t need = vm & nzm;
+                if (need & 0xFFFFu) {
                     uint32_t c[W];
-                    if (cob(pv, qa[h], qb[h], c)) best = 1u;
-                } else if (pany) best = 1u;
+                    if (cob(pv, (int)(qx[k] & 0xFFFFu), (int)(qy[k] & 0xFFFFu), c)) best = 1u;
+                }
+                if (need >> 16) {
+                    uint32_t c[W];
+                    if (cob(pv, (int)(qx[k] >> 16), (int)(qy[k] >> 16), c)) best = 1u;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int h = 0; h < APT; ++h) {
+                if (ta[h] < (uint32_t)pr && tb[h] < (uint32_t)pr) {
+                    if (qa[h] | qb[h]) {
+                        uint32_t c[W];
+                        if (cob(pv, qa[h], qb[h], c)) best = 1u;
+                    } else if (pany) best = 1u;
+                }
             }
         }
         const uint32_t top = block_max_u32<NTH>(best, red);
