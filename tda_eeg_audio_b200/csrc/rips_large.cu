@@ -1199,6 +1199,32 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
         for (int w = 0; w < W; ++w) { pe[w] &= live[w]; any |= pe[w]; }
         return any != 0;
     }
+    // 16-bit ranks: this thread's APT consecutive apexes of the rank rows of x and y and of their index rows, two per
+    // word (one 8- or 16-byte load per row; the padding of a row is "absent" / 0, rank_small_kernel)
+    static constexpr bool kVec = sizeof(TT) == 2 && (APT == 4 || APT == 8);
+    static constexpr int NPK = kVec ? APT / 2 : 1;
+    __device__ __forceinline__ void load_rows_packed(int x, int y, uint32_t (&a)[NPK], uint32_t (&b)[NPK],
+                                                     uint32_t (&qx)[NPK], uint32_t (&qy)[NPK]) const {
+        const TT* Tx = T + (size_t)x * ldT;
+        const TT* Ty = T + (size_t)y * ldT;
+        const uint16_t* Qx = Q + (size_t)x * ldT;
+        const uint16_t* Qy = Q + (size_t)y * ldT;
+#pragma unroll
+        for (int k = 0; k < NPK; ++k) { a[k] = 0xFFFFFFFFu; b[k] = 0xFFFFFFFFu; qx[k] = 0u; qy[k] = 0u; }
+        if (APT * tid < ldT) {
+            if constexpr (APT == 4) {
+                const uint2 ta2 = __ldg(reinterpret_cast<const uint2*>(Tx) + tid), tb2 = __ldg(reinterpret_cast<const uint2*>(Ty) + tid);
+                const uint2 qx2 = reinterpret_cast<const uint2*>(Qx)[tid], qy2 = reinterpret_cast<const uint2*>(Qy)[tid];
+                a[0] = ta2.x; a[1] = ta2.y; b[0] = tb2.x; b[1] = tb2.y;
+                qx[0] = qx2.x; qx[1] = qx2.y; qy[0] = qy2.x; qy[1] = qy2.y;
+            } else if constexpr (APT == 8) {
+                const uint4 ta4 = __ldg(reinterpret_cast<const uint4*>(Tx) + tid), tb4 = __ldg(reinterpret_cast<const uint4*>(Ty) + tid);
+                const uint4 qx4 = reinterpret_cast<const uint4*>(Qx)[tid], qy4 = reinterpret_cast<const uint4*>(Qy)[tid];
+                a[0] = ta4.x; a[1] = ta4.y; a[2] = ta4.z; a[3] = ta4.w; b[0] = tb4.x; b[1] = tb4.y; b[2] = tb4.z; b[3] = tb4.w;
+                qx[0] = qx4.x; qx[1] = qx4.y; qx[2] = qx4.z; qx[3] = qx4.w; qy[0] = qy4.x; qy[1] = qy4.y; qy[2] = qy4.z; qy[3] = qy4.w;
+            }
+        }
+    }
     // death loop over the visited edges act[0 .. na); (spr, spq): rank and P word when the run is one edge
     __device__ void step_b(int r0, int r1, int spr = -1, uint32_t spq = 0u) {
         const int na = ctl[1];
@@ -1217,11 +1243,16 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
                 // chain of global round trips otherwise (rank -> index -> compact entry, per apex)
                 const int qe = Qx[y];
                 uint32_t ta[APT], tb[APT], qq[APT];
+                uint32_t ra[NPK], rb[NPK], qx[NPK], qy[NPK];
+                if constexpr (kVec) {
+                    load_rows_packed(x, y, ra, rb, qx, qy);
+                } else {
 #pragma unroll
-                for (int h = 0; h < APT; ++h) {
-                    const int z = tid + h * NTH;
-                    ta[h] = kAbsent; tb[h] = kAbsent; qq[h] = 0u;
-                    if (z < n) { ta[h] = __ldg(Tx + z); tb[h] = __ldg(Ty + z); qq[h] = (uint32_t)Qx[z] | ((uint32_t)Qy[z] << 16); }
+                    for (int h = 0; h < APT; ++h) {
+                        const int z = tid + h * NTH;
+                        ta[h] = kAbsent; tb[h] = kAbsent; qq[h] = 0u;
+                        if (z < n) { ta[h] = __ldg(Tx + z); tb[h] = __ldg(Ty + z); qq[h] = (uint32_t)Qx[z] | ((uint32_t)Qy[z] << 16); }
+                    }
                 }
                 uint32_t pe[W];
 #pragma unroll
@@ -1233,13 +1264,31 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
                 // this thread's apexes from the largest down: the first triangle with a non-zero mask is its
                 // candidate for this edge (the index grows with the apex)
                 int zhit = -1;
+                if constexpr (kVec) {
+                    const uint32_t pr2 = (uint32_t)pr * 0x10001u;
 #pragma unroll
-                for (int h = APT - 1; h >= 0; --h) {
-                    if (zhit < 0 && ta[h] < (uint32_t)pr && tb[h] < (uint32_t)pr) {
-                        if (qq[h]) {
-                            uint32_t c[W];
-                            if (cob(pe, (int)(qq[h] & 0xFFFFu), (int)(qq[h] >> 16), c)) zhit = tid + h * NTH;
-                        } else if (pany) zhit = tid + h * NTH;   // both other edges carry 0: the mask is the edge's own value
+                    for (int k = NPK - 1; k >= 0; --k) {
+                        const uint32_t vm = __vcmpltu2(__vmaxu2(ra[k], rb[k]), pr2);
+#pragma unroll
+                        for (int hf = 1; hf >= 0; --hf) {
+                            if (zhit < 0 && ((vm >> (16 * hf)) & 0xFFFFu)) {
+                                const int qa = (int)((qx[k] >> (16 * hf)) & 0xFFFFu), qb = (int)((qy[k] >> (16 * hf)) & 0xFFFFu);
+                                if (qa | qb) {
+                                    uint32_t c[W];
+                                    if (cob(pe, qa, qb, c)) zhit = APT * tid + 2 * k + hf;
+                                } else if (pany) zhit = APT * tid + 2 * k + hf;
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int h = APT - 1; h >= 0; --h) {
+                        if (zhit < 0 && ta[h] < (uint32_t)pr && tb[h] < (uint32_t)pr) {
+                            if (qq[h]) {
+                                uint32_t c[W];
+                                if (cob(pe, (int)(qq[h] & 0xFFFFu), (int)(qq[h] >> 16), c)) zhit = tid + h * NTH;
+                            } else if (pany) zhit = tid + h * NTH;   // both other edges carry 0: the mask is the edge's own value
+                        }
                     }
                 }
                 if (zhit >= 0) {
@@ -1366,26 +1415,9 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
         // apex of (thread, h): four CONSECUTIVE apexes per thread when the ranks are 16-bit (clouds up to
         // 256 points: NTH * 4 covers the padded row), so each of the four rows is one 8-byte load per thread;
         // the padding of a row is "absent" in T and 0 in Q (rank_small_kernel), no bounds test needed
-        constexpr bool kVec = sizeof(TT) == 2 && (APT == 4 || APT == 8);
-        constexpr int NPK = kVec ? APT / 2 : 1;
         uint32_t a[NPK], b[NPK], qx[NPK], qy[NPK];   // kVec: two 16-bit ranks / indices per word, kept packed
         if constexpr (kVec) {
-            // APT consecutive apexes per thread: each of the four rows is one 8- or 16-byte load per thread
-#pragma unroll
-            for (int k = 0; k < APT / 2; ++k) { a[k] = 0xFFFFFFFFu; b[k] = 0xFFFFFFFFu; qx[k] = 0u; qy[k] = 0u; }
-            if (APT * tid < ldT) {
-                if constexpr (APT == 4) {
-                    const uint2 ta2 = __ldg(reinterpret_cast<const uint2*>(Tx) + tid), tb2 = __ldg(reinterpret_cast<const uint2*>(Ty) + tid);
-                    const uint2 qx2 = reinterpret_cast<const uint2*>(Qx)[tid], qy2 = reinterpret_cast<const uint2*>(Qy)[tid];
-                    a[0] = ta2.x; a[1] = ta2.y; b[0] = tb2.x; b[1] = tb2.y;
-                    qx[0] = qx2.x; qx[1] = qx2.y; qy[0] = qy2.x; qy[1] = qy2.y;
-                } else {
-                    const uint4 ta4 = __ldg(reinterpret_cast<const uint4*>(Tx) + tid), tb4 = __ldg(reinterpret_cast<const uint4*>(Ty) + tid);
-                    const uint4 qx4 = reinterpret_cast<const uint4*>(Qx)[tid], qy4 = reinterpret_cast<const uint4*>(Qy)[tid];
-                    a[0] = ta4.x; a[1] = ta4.y; a[2] = ta4.z; a[3] = ta4.w; b[0] = tb4.x; b[1] = tb4.y; b[2] = tb4.z; b[3] = tb4.w;
-                    qx[0] = qx4.x; qx[1] = qx4.y; qx[2] = qx4.z; qx[3] = qx4.w; qy[0] = qy4.x; qy[1] = qy4.y; qy[2] = qy4.z; qy[3] = qy4.w;
-                }
-            }
+            load_rows_packed(x, y, a, b, qx, qy);
         } else {
 #pragma unroll
             for (int h = 0; h < APT; ++h) {
