@@ -1213,13 +1213,15 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
         for (int k = 0; k < NPK; ++k) { a[k] = 0xFFFFFFFFu; b[k] = 0xFFFFFFFFu; qx[k] = 0u; qy[k] = 0u; }
         if (APT * tid < ldT) {
             if constexpr (APT == 4) {
-                const uint2 ta2 = __ldg(reinterpret_cast<const uint2*>(Tx) + tid), tb2 = __ldg(reinterpret_cast<const uint2*>(Ty) + tid);
-                const uint2 qx2 = reinterpret_cast<const uint2*>(Qx)[tid], qy2 = reinterpret_cast<const uint2*>(Qy)[tid];
+                // (streaming loads: the ~1 GB of rank / index tables of the resident clouds should not push the compact
+                // stores of the CTAs -- a few KB each, re-used cloud after cloud -- out of L2)
+                const uint2 ta2 = __ldcs(reinterpret_cast<const uint2*>(Tx) + tid), tb2 = __ldcs(reinterpret_cast<const uint2*>(Ty) + tid);
+                const uint2 qx2 = __ldcs(reinterpret_cast<const uint2*>(Qx) + tid), qy2 = __ldcs(reinterpret_cast<const uint2*>(Qy) + tid);
                 a[0] = ta2.x; a[1] = ta2.y; b[0] = tb2.x; b[1] = tb2.y;
                 qx[0] = qx2.x; qx[1] = qx2.y; qy[0] = qy2.x; qy[1] = qy2.y;
             } else if constexpr (APT == 8) {
-                const uint4 ta4 = __ldg(reinterpret_cast<const uint4*>(Tx) + tid), tb4 = __ldg(reinterpret_cast<const uint4*>(Ty) + tid);
-                const uint4 qx4 = reinterpret_cast<const uint4*>(Qx)[tid], qy4 = reinterpret_cast<const uint4*>(Qy)[tid];
+                const uint4 ta4 = __ldcs(reinterpret_cast<const uint4*>(Tx) + tid), tb4 = __ldcs(reinterpret_cast<const uint4*>(Ty) + tid);
+                const uint4 qx4 = __ldcs(reinterpret_cast<const uint4*>(Qx) + tid), qy4 = __ldcs(reinterpret_cast<const uint4*>(Qy) + tid);
                 a[0] = ta4.x; a[1] = ta4.y; a[2] = ta4.z; a[3] = ta4.w; b[0] = tb4.x; b[1] = tb4.y; b[2] = tb4.z; b[3] = tb4.w;
                 qx[0] = qx4.x; qx[1] = qx4.y; qx[2] = qx4.z; qx[3] = qx4.w; qy[0] = qy4.x; qy[1] = qy4.y; qy[2] = qy4.z; qy[3] = qy4.w;
             }
@@ -1519,7 +1521,7 @@ template <int NTH, int APT, int W, bool SG, typename TT> struct Sweep {
             {
                 const int rn = rr + NTH;
                 pe_nx = kMst; dv_nx = 0;
-                if (rn < m) { pe_nx = __ldg(P + rn); dv_nx = defv[rn]; }
+                if (rn < m) { pe_nx = __ldcs(P + rn); dv_nx = __ldcs(defv + rn); }
                 if constexpr (NTH == 32) {
                     // a chunk without a visited edge is over in a few instructions: the edge words further ahead
                     // are requested from DRAM eight chunks early (one 128-byte line of P, half a line of defv)
