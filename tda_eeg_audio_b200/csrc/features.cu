@@ -20,7 +20,7 @@ namespace features {
 
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 
-// reductions over the LPD lanes that share a diagram (LPD = 16: two diagrams per warp)
+// reductions over the LPD lanes that share a diagram (LPD = 4: eight diagrams per warp)
 template <int LPD> __device__ __forceinline__ double wsum(double v) {
 #pragma unroll
     for (int o = LPD / 2; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
@@ -37,9 +37,10 @@ template <int LPD> __device__ __forceinline__ int wsumi(int v) {
     return v;
 }
 
-// The kernel is issue-bound (float64 logarithm, division and the nine shuffle reductions per diagram), and a
-// diagram of a 47-channel window has 46 + ~37 rows: with a whole warp per diagram most lanes idle in the second
-// trip.  Sixteen lanes per diagram halve the instructions per diagram (0.95 -> 0.5 ms per 849,600 diagrams).
+// The kernel is issue-bound (float64 logarithm, division, square roots and the nine shuffle reductions per
+// diagram), and a diagram of a 47-channel window has 46 + ~37 rows: with a whole warp per diagram most lanes idled
+// in the second trip and every diagram paid a full warp's reductions and epilogue.  Measured per 849,600 diagrams:
+// 32 lanes per diagram 0.95 ms, 16: 0.57, 8: 0.40, 4: 0.32, 2: 0.29 -- four lanes (eight diagrams per warp) it is.
 template <int LPD>
 __global__ void __launch_bounds__(256) pers_features_kernel(const float* __restrict__ bd, int cap,
                                                             const int* __restrict__ counts, int count_stride,
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(256) pers_features_kernel(const float* __restr
         vb = wsum<LPD>(vb); vd = wsum<LPD>(vd); vp = wsum<LPD>(vp); ent = wsum<LPD>(ent);
         if (!have) continue;   // (after the last shuffle: both halves of the warp take part in every one)
         if (nf == 0) {
-            if (l < 11) o[l] = (l == 1) ? (double)n : 0.0;
+            for (int q = l; q < 11; q += LPD) o[q] = (q == 1) ? (double)n : 0.0;
         } else if (l == 0) {
             const bool many = nf > 1;
             o[0] = nf;
@@ -141,12 +142,12 @@ extern "C" int tda_pers_features(const float* bd, int cap, const int* counts, in
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // sixteen lanes per diagram whatever its size: the summation order, and with it the last bits of the features,
+    // four lanes per diagram whatever its size: the summation order, and with it the last bits of the features,
     // must not depend on the padding `cap` the caller happened to choose
-    long long need = ((long long)B + 15) / 16;
+    long long need = ((long long)B + 63) / 64;
     int grid = (int)(need < (long long)sms * 8 ? need : (long long)sms * 8);
     tda::ProfScope prof("pers_features", (cudaStream_t)stream);
-    tda::features::pers_features_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(bd, cap, counts, count_stride, B,
+    tda::features::pers_features_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(bd, cap, counts, count_stride, B,
                                                                                     feats, feat_stride);
     tda::count_launch();
     return (int)cudaGetLastError();
