@@ -31,6 +31,12 @@
 // same kernel: costs are evaluated where they are needed (the same expression, so the result is bit-identical),
 // the "column used" flags live in shared memory instead of one register bit per column, and what remains in
 // shared memory is linear in the number of points (up to ~4,000 points per pair).
+//
+// Two launches per batch (MODE 1, then MODE 2): the dynamic programme needs memory linear in the diagram sizes, the
+// assignment solver a cost block of up to 227 KB, and a launch sized for the block leaves two warps on an SM.  The
+// first launch (linear shared memory, a dozen warps per SM and more) solves every one-dimensional pair and marks the
+// others in `out` with a NaN of its own; the second, sized for the block, takes only the marked pairs.  A batch of
+// H0 diagrams (46 EEG bars against 100-250 audio bars) never reaches the second kernel's solver.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -104,7 +110,13 @@ __device__ int load_diagram(const TIn* __restrict__ bd, int n, int cap, double* 
     return m;
 }
 
-template <typename TIn, bool BIG>
+// "not a one-dimensional pair: left to the assignment solver" (a quiet NaN no computation produces: costs are finite)
+__device__ __forceinline__ double pending_mark() { return __longlong_as_double(0x7FF8DEADBEEF0001LL); }
+__device__ __forceinline__ bool is_pending(double v) { return __double_as_longlong(v) == 0x7FF8DEADBEEF0001LL; }
+
+// MODE 0: everything in one launch (the BIG variant); 1: one-dimensional pairs only, the others are marked;
+// 2: the marked pairs only
+template <typename TIn, bool BIG, int MODE>
 __global__ void __launch_bounds__(32) wasserstein_kernel(Params<TIn> p) {
     extern __shared__ __align__(16) unsigned char wsm[];
     const int lane = threadIdx.x;
@@ -122,6 +134,11 @@ __global__ void __launch_bounds__(32) wasserstein_kernel(Params<TIn> p) {
     const double cs = 0.7071067811865476, sn = 0.7071067811865475;  // np.cos(pi/4), np.sin(pi/4)
 
     for (long long k = blockIdx.x; k < p.B; k += gridDim.x) {
+        if constexpr (MODE == 2) {
+            double cur = 0.0;
+            if (lane == 0) cur = p.out[k];
+            if (!is_pending(__shfl_sync(kFull, cur, 0))) continue;
+        }
         const long long ia = p.idxA ? p.idxA[k] : k;
         const long long ib = p.idxB ? p.idxB[k] : k;
         // the diagram with fewer rows becomes S (rows of the assignment); the problem is symmetric
@@ -142,7 +159,7 @@ __global__ void __launch_bounds__(32) wasserstein_kernel(Params<TIn> p) {
         for (int j = lane; j < N; j += 32) dT[j] = -T[2 * j] * sn + T[2 * j + 1] * cs;
         __syncwarp();
         // ---- one-dimensional pair (all births equal, deaths sorted)?  then the dynamic programme
-        {
+        if constexpr (MODE != 2) {
             const double b0 = S[0];
             bool ok = true;
             for (int i = lane; i < M; i += 32) ok &= S[2 * i] == b0 && (i == 0 || S[2 * i + 1] >= S[2 * i - 1]);
@@ -196,6 +213,11 @@ __global__ void __launch_bounds__(32) wasserstein_kernel(Params<TIn> p) {
                 __syncwarp();
                 continue;
             }
+        }
+        if constexpr (MODE == 1) {
+            if (lane == 0) p.out[k] = pending_mark();
+            __syncwarp();
+            continue;
         }
         if constexpr (!BIG) {
             for (int e = lane; e < M * N; e += 32) {
@@ -294,22 +316,34 @@ static int launch(const TIn* bdA, const int* nA, int nA_stride, int capA, int li
     p.cols_cap = ca < cb ? cb : ca;
     size_t smem = smem_bytes(p.rows_cap, p.cols_cap);
     const bool big = p.rows_cap + p.cols_cap + 1 > 1024 || smem > 227 * 1024;
-    if (big) smem = smem_bytes(p.rows_cap, p.cols_cap, true);
-    if (smem > 227 * 1024) return TDA_E_SIZE;   // more than ~4,000 points in a pair
-    cudaError_t e = big ? cudaFuncSetAttribute(wasserstein_kernel<TIn, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                        : cudaFuncSetAttribute(wasserstein_kernel<TIn, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    const size_t smem_lin = smem_bytes(p.rows_cap, p.cols_cap, true);
+    if (smem_lin > 227 * 1024) return TDA_E_SIZE;   // more than ~4,000 points in a pair
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int per_sm = (int)((227 * 1024) / (smem + 1024));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 32) per_sm = 32;
-    long long grid = (long long)sms * per_sm;
-    if (grid > B) grid = B;
-    tda::ProfScope prof("wasserstein", (cudaStream_t)stream);
-    if (big) wasserstein_kernel<TIn, true><<<(int)grid, 32, smem, (cudaStream_t)stream>>>(p);
-    else wasserstein_kernel<TIn, false><<<(int)grid, 32, smem, (cudaStream_t)stream>>>(p);
+    auto grid_for = [&](size_t sm_bytes) {
+        int per_sm = (int)((227 * 1024) / (sm_bytes + 1024));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 32) per_sm = 32;
+        long long g = (long long)sms * per_sm;
+        return (int)(g > B ? B : g);
+    };
+    cudaStream_t st = (cudaStream_t)stream;
+    tda::ProfScope prof("wasserstein", st);
+    cudaError_t e;
+    if (big) {   // costs on the fly, linear shared memory: one launch does both kinds of pairs
+        e = cudaFuncSetAttribute(wasserstein_kernel<TIn, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lin);
+        if (e != cudaSuccess) return (int)e;
+        wasserstein_kernel<TIn, true, 0><<<grid_for(smem_lin), 32, smem_lin, st>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(wasserstein_kernel<TIn, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lin);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(wasserstein_kernel<TIn, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        wasserstein_kernel<TIn, true, 1><<<grid_for(smem_lin), 32, smem_lin, st>>>(p);
+        tda::count_launch();
+        wasserstein_kernel<TIn, false, 2><<<grid_for(smem), 32, smem, st>>>(p);
+    }
     tda::count_launch();
     return (int)cudaGetLastError();
 }
