@@ -231,10 +231,8 @@ int tda_pairwise_dist_f32(const double* pts, const int* npts, long long B, int l
  * diagram counts as the single point (0,0), as safe_wasserstein does.  Pair k compares diagram
  * idxA[k] of A with diagram idxB[k] of B (NULL => k), so matched and mismatched pairings need no
  * copies.  out[k] float64.  limA / limB (0 => the cap) are upper bounds on the row counts actually
- * present (rows beyond them are ignored); shared memory is sized by them: while
- * 8 * min(limA,limB) * max(limA,limB) bytes fit in 227 KB and limA + limB <= 1022 the cost block of a
- * pair is kept in shared memory; beyond that the same solver evaluates the costs where it needs them
- * (identical arithmetic, identical result, slower) up to ~4,000 points per pair, then TDA_E_SIZE. */
+ * present (rows beyond them are ignored); shared memory is sized by them and linear in limA + limB
+ * (about 57 bytes per point: up to ~4,000 points per pair, then TDA_E_SIZE). */
 int tda_wasserstein_batched(const float* bdA, const int* nA, int nA_stride, int capA, int limA,
                             const float* bdB, const int* nB, int nB_stride, int capB, int limB,
                             const int* idxA, const int* idxB, long long B, double* out, void* stream);

@@ -11,9 +11,9 @@
 // That optimum equals  sum_j dt_j + min over assignments of the M points of S to either a point
 // of T (reduced cost c_ij - dt_j) or their own diagonal (cost ds_i): an M x (N+M) rectangular
 // assignment problem whose diagonal block is implicit.  One warp solves one pair with the
-// shortest-augmenting-path (Hungarian with potentials) algorithm: the M x N block of L2 costs
-// lives in the warp's shared memory in float64 (M <= N after an optional role swap), lanes stride
-// over the columns for the relax + arg-min step.  The optimum of an LSAP is unique in value, so
+// shortest-augmenting-path (Hungarian with potentials) algorithm: points, potentials and the column
+// flags live in the warp's shared memory in float64 (M <= N after an optional role swap), the L2 costs
+// are evaluated where they are needed, lanes stride over the columns for the relax + arg-min step.  The optimum of an LSAP is unique in value, so
 // the result matches scipy's to rounding.
 //
 // H0 diagrams are one-dimensional: every birth is 0 and the deaths come sorted.  For such a pair (all
@@ -26,17 +26,15 @@
 // are the very same Gram-trick values.  46 x 113 cells instead of O(M^2 N) augmentation steps:
 // 19,200 EEG-vs-audio H0 pairs in 13.1 ms before (profiles/r02_wasserstein_h0_ncu.json).
 //
-// Pairs whose cost block does not fit an SM's shared memory (two diagrams of a few hundred points each: the
-// H0 diagrams of two 248-point clouds, anything from the 1,000-2,000-point clouds) take the BIG variant of the
-// same kernel: costs are evaluated where they are needed (the same expression, so the result is bit-identical),
-// the "column used" flags live in shared memory instead of one register bit per column, and what remains in
-// shared memory is linear in the number of points (up to ~4,000 points per pair).
+// Shared memory is linear in the number of points of a pair (up to ~4,000 points): the solver's costs are not
+// stored.  Round 2 first kept the M x N cost block of a pair in shared memory -- 93 KB for 46 EEG bars against
+// 248 audio bars, two warps per SM -- and measured the on-the-fly variant (a dozen warps per SM and more) faster
+// on every batch of the pipeline, with bit-identical results (the same expression); the block is gone.
 //
-// Two launches per batch (MODE 1, then MODE 2): the dynamic programme needs memory linear in the diagram sizes, the
-// assignment solver a cost block of up to 227 KB, and a launch sized for the block leaves two warps on an SM.  The
-// first launch (linear shared memory, a dozen warps per SM and more) solves every one-dimensional pair and marks the
-// others in `out` with a NaN of its own; the second, sized for the block, takes only the marked pairs.  A batch of
-// H0 diagrams (46 EEG bars against 100-250 audio bars) never reaches the second kernel's solver.
+// Two launches per batch (MODE 1, then MODE 2): the first solves every one-dimensional pair with the dynamic
+// programme and marks the others in `out` with a NaN of its own; the second runs the solver on the marked pairs
+// only.  A batch of H0 diagrams never reaches the solver, and a warp of the first launch is not held up behind a
+// neighbour's O(M^2 N) augmentations.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -59,16 +57,15 @@ template <typename TIn> struct Params {
     int rows_cap, cols_cap;  // min / max of the two caps (+1 for the placeholder point)
 };
 
-__host__ __device__ inline size_t smem_bytes(int rows_cap, int cols_cap, bool big = false) {
+__host__ __device__ inline size_t smem_bytes(int rows_cap, int cols_cap) {
     size_t s = 0;
-    // cost block (+ slack: a row of the 1-D programme has cols + 1 entries); BIG: that row only
-    s += big ? ((size_t)cols_cap + 2) * 8 : ((size_t)rows_cap * cols_cap + 2) * 8;
+    s += ((size_t)cols_cap + 2) * 8;               // one row of the 1-D programme (cols + 1 entries)
     s += (size_t)2 * (rows_cap + cols_cap) * 8;    // points S, T  (x, y)
     s += (size_t)(rows_cap + cols_cap) * 8;        // ds, dt
     s += (size_t)(rows_cap + 1) * 8;               // u
     s += (size_t)2 * (rows_cap + cols_cap + 1) * 8; // v, minv
     s += (size_t)2 * (rows_cap + cols_cap + 1) * 4; // p, way
-    if (big) s += (size_t)(rows_cap + cols_cap + 4);   // column-used flags
+    s += (size_t)(rows_cap + cols_cap + 4);        // column-used flags
     return (s + 15) & ~(size_t)15;
 }
 
@@ -114,15 +111,14 @@ __device__ int load_diagram(const TIn* __restrict__ bd, int n, int cap, double* 
 __device__ __forceinline__ double pending_mark() { return __longlong_as_double(0x7FF8DEADBEEF0001LL); }
 __device__ __forceinline__ bool is_pending(double v) { return __double_as_longlong(v) == 0x7FF8DEADBEEF0001LL; }
 
-// MODE 0: everything in one launch (the BIG variant); 1: one-dimensional pairs only, the others are marked;
-// 2: the marked pairs only
-template <typename TIn, bool BIG, int MODE>
+// MODE 1: one-dimensional pairs only, the others are marked; 2: the marked pairs only
+template <typename TIn, int MODE>
 __global__ void __launch_bounds__(32) wasserstein_kernel(Params<TIn> p) {
     extern __shared__ __align__(16) unsigned char wsm[];
     const int lane = threadIdx.x;
     const int RC = p.rows_cap, CC = p.cols_cap;
     double* cost = (double*)wsm;
-    double* PA = cost + (BIG ? (size_t)CC : (size_t)RC * CC) + 2;   // points of A, then points of B right behind them
+    double* PA = cost + (size_t)CC + 2;   // points of A, then points of B right behind them
     double* dS = PA + 2 * (size_t)(RC + CC);
     double* dT = dS + RC;
     double* u = dT + CC;
@@ -130,7 +126,7 @@ __global__ void __launch_bounds__(32) wasserstein_kernel(Params<TIn> p) {
     double* minv = v + (RC + CC + 1);
     int* pcol = (int*)(minv + (RC + CC + 1));
     int* way = pcol + (RC + CC + 1);
-    unsigned char* usedf = (unsigned char*)(way + (RC + CC + 1));   // BIG only
+    unsigned char* usedf = (unsigned char*)(way + (RC + CC + 1));   // column-used flags of the solver
     const double cs = 0.7071067811865476, sn = 0.7071067811865475;  // np.cos(pi/4), np.sin(pi/4)
 
     for (long long k = blockIdx.x; k < p.B; k += gridDim.x) {
@@ -219,12 +215,6 @@ __global__ void __launch_bounds__(32) wasserstein_kernel(Params<TIn> p) {
             __syncwarp();
             continue;
         }
-        if constexpr (!BIG) {
-            for (int e = lane; e < M * N; e += 32) {
-                const int i = e / N, j = e % N;
-                cost[(size_t)i * N + j] = ground_cost(S, T, i, j);
-            }
-        }
         const int Mc = N + M;  // columns: N real + M private diagonal columns
         for (int j = lane; j <= Mc; j += 32) { v[j] = 0.0; pcol[j] = 0; }
         for (int i = lane; i <= M; i += 32) u[i] = 0.0;
@@ -233,22 +223,19 @@ __global__ void __launch_bounds__(32) wasserstein_kernel(Params<TIn> p) {
         for (int i = 1; i <= M; ++i) {
             if (lane == 0) pcol[0] = i;
             for (int j = lane; j <= Mc; j += 32) minv[j] = kInf;
-            // used[] as a bitmask in registers: lane owns columns j = lane + 32 t
-            uint32_t used = 0;  // bit t <-> column lane + 32 t   (Mc <= 32*32; BIG: byte flags in shared memory)
-            if constexpr (BIG) { for (int j = lane; j <= Mc; j += 32) usedf[j] = 0; }
+            for (int j = lane; j <= Mc; j += 32) usedf[j] = 0;
             __syncwarp();
             int j0 = 0;
             while (true) {
-                if constexpr (BIG) { if (lane == (j0 & 31)) usedf[j0] = 1; }
-                else { if (lane == (j0 & 31)) used |= 1u << (j0 >> 5); }
+                if (lane == (j0 & 31)) usedf[j0] = 1;
                 const int i0 = pcol[j0];
                 const double ui0 = u[i0];
                 double best = kInf;
                 int bestj = -1;
-                for (int j = lane, t = 0; j <= Mc; j += 32, ++t) {
-                    if (j == 0 || (BIG ? usedf[j] != 0 : ((used >> t) & 1u) != 0)) continue;
+                for (int j = lane; j <= Mc; j += 32) {
+                    if (j == 0 || usedf[j] != 0) continue;
                     double a;
-                    if (j <= N) a = (BIG ? ground_cost(S, T, i0 - 1, j - 1) : cost[(size_t)(i0 - 1) * N + (j - 1)]) - dT[j - 1];
+                    if (j <= N) a = ground_cost(S, T, i0 - 1, j - 1) - dT[j - 1];
                     else a = (j - N == i0) ? dS[i0 - 1] : kInf;
                     const double cur = a - ui0 - v[j];
                     double mv = minv[j];
@@ -263,8 +250,8 @@ __global__ void __launch_bounds__(32) wasserstein_kernel(Params<TIn> p) {
                     if (ob < best || (ob == best && oj >= 0 && (bestj < 0 || oj < bestj))) { best = ob; bestj = oj; }
                 }
                 const double delta = best;
-                for (int j = lane, t = 0; j <= Mc; j += 32, ++t) {
-                    if (BIG ? usedf[j] != 0 : ((used >> t) & 1u) != 0) { u[pcol[j]] += delta; v[j] -= delta; }
+                for (int j = lane; j <= Mc; j += 32) {
+                    if (usedf[j] != 0) { u[pcol[j]] += delta; v[j] -= delta; }
                     else minv[j] -= delta;
                 }
                 __syncwarp();
@@ -282,7 +269,7 @@ __global__ void __launch_bounds__(32) wasserstein_kernel(Params<TIn> p) {
         double tot = 0.0;
         for (int j = lane + 1; j <= Mc; j += 32) {
             const int i = pcol[j];
-            if (j <= N) tot += (i > 0) ? (BIG ? ground_cost(S, T, i - 1, j - 1) : cost[(size_t)(i - 1) * N + (j - 1)]) : dT[j - 1];
+            if (j <= N) tot += (i > 0) ? ground_cost(S, T, i - 1, j - 1) : dT[j - 1];
             else if (i > 0) tot += dS[i - 1];
         }
 #pragma unroll
@@ -314,36 +301,25 @@ static int launch(const TIn* bdA, const int* nA, int nA_stride, int capA, int li
     const int ca = limA < 1 ? 1 : limA, cb = limB < 1 ? 1 : limB;
     p.rows_cap = ca < cb ? ca : cb;
     p.cols_cap = ca < cb ? cb : ca;
-    size_t smem = smem_bytes(p.rows_cap, p.cols_cap);
-    const bool big = p.rows_cap + p.cols_cap + 1 > 1024 || smem > 227 * 1024;
-    const size_t smem_lin = smem_bytes(p.rows_cap, p.cols_cap, true);
-    if (smem_lin > 227 * 1024) return TDA_E_SIZE;   // more than ~4,000 points in a pair
+    const size_t smem = smem_bytes(p.rows_cap, p.cols_cap);
+    if (smem > 227 * 1024) return TDA_E_SIZE;   // more than ~4,000 points in a pair
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    auto grid_for = [&](size_t sm_bytes) {
-        int per_sm = (int)((227 * 1024) / (sm_bytes + 1024));
-        if (per_sm < 1) per_sm = 1;
-        if (per_sm > 32) per_sm = 32;
-        long long g = (long long)sms * per_sm;
-        return (int)(g > B ? B : g);
-    };
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 32) per_sm = 32;
+    long long grid = (long long)sms * per_sm;
+    if (grid > B) grid = B;
     cudaStream_t st = (cudaStream_t)stream;
     tda::ProfScope prof("wasserstein", st);
-    cudaError_t e;
-    if (big) {   // costs on the fly, linear shared memory: one launch does both kinds of pairs
-        e = cudaFuncSetAttribute(wasserstein_kernel<TIn, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lin);
-        if (e != cudaSuccess) return (int)e;
-        wasserstein_kernel<TIn, true, 0><<<grid_for(smem_lin), 32, smem_lin, st>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(wasserstein_kernel<TIn, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lin);
-        if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(wasserstein_kernel<TIn, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        wasserstein_kernel<TIn, true, 1><<<grid_for(smem_lin), 32, smem_lin, st>>>(p);
-        tda::count_launch();
-        wasserstein_kernel<TIn, false, 2><<<grid_for(smem), 32, smem, st>>>(p);
-    }
+    cudaError_t e = cudaFuncSetAttribute(wasserstein_kernel<TIn, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(wasserstein_kernel<TIn, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    wasserstein_kernel<TIn, 1><<<(int)grid, 32, smem, st>>>(p);
+    tda::count_launch();
+    wasserstein_kernel<TIn, 2><<<(int)grid, 32, smem, st>>>(p);
     tda::count_launch();
     return (int)cudaGetLastError();
 }

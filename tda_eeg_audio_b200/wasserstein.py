@@ -12,10 +12,8 @@ def wasserstein_batched(bdA, nA, bdB, nB, idxA=None, idxB=None, out=None, limA=N
     output) or both float64; nA / nB CUDA int32 1-D (strided views such as counts[:, 1] are fine).
     Returns CUDA float64 (K,), K = len(idxA) or BA.
 
-    Capacity (include/tda_b200.h): while 8 * min * max bytes of the largest diagram pair fit 227 KB of
-    shared memory and limA + limB <= 1022 the cost block of a pair sits in shared memory; beyond that
-    the same solver evaluates costs on the fly (same result, slower) up to ~4,000 points per pair, and
-    only then the call raises TdaError (TDA_E_SIZE)."""
+    Capacity (include/tda_b200.h): shared memory is linear in the sizes of the largest pair (about 57 bytes
+    per point): up to ~4,000 points per pair, beyond that the call raises TdaError (TDA_E_SIZE)."""
     import torch
     _lib.require_cuda()
     assert bdA.is_cuda and bdB.is_cuda and bdA.dtype == bdB.dtype and bdA.dtype in (torch.float32, torch.float64)

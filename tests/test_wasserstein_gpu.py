@@ -99,10 +99,10 @@ def test_one_dimensional_pairs_take_the_dynamic_programme_and_agree(cuda):
         assert abs(got2[k] - want) <= 1e-9 * max(1.0, abs(want)), (k, got2[k], want)
 
 
-def test_pairs_beyond_the_shared_memory_cost_block(cuda):
-    """Two diagrams of a few hundred points each (H1 of big clouds; H0 of two 248-point clouds) do not fit
-    the shared-memory cost block: the solver then evaluates the costs on the fly -- same arithmetic, so the
-    result must be the very number the cost-block variant gives where both apply, and scipy's otherwise."""
+def test_large_pairs_and_independence_of_the_batch_caps(cuda):
+    """Two diagrams of a few hundred points each (H1 of big clouds; H0 of two 248-point clouds): shared memory
+    is linear in the sizes of a pair, so these run like any other pair and must agree with scipy; and the
+    result of a pair must not depend on the capacities (padding) of the batch it travels in."""
     import torch
     from oracle import wasserstein_ref
     from tda_eeg_audio_b200.wasserstein import wasserstein, wasserstein_batched
@@ -120,7 +120,7 @@ def test_pairs_beyond_the_shared_memory_cost_block(cuda):
     for k in range(K):
         want = wasserstein_ref.safe_wasserstein(A[k, :nA[k]].astype(np.float64), B[k, :nB[k]].astype(np.float64))
         assert abs(got[k] - want) <= 1e-9 * max(1.0, abs(want)), (k, got[k], want)
-    # (b) bit-identical to the cost-block variant: the same small pair inside a batch with big caps and alone
+    # (b) bit-identical whatever the caps: the same small pair inside a batch with big caps and alone
     a = _rand_dgm(rng, 40); b = _rand_dgm(rng, 90, 0.6)
     A2 = np.zeros((1, 600, 2), np.float32); B2 = np.zeros((1, 600, 2), np.float32)
     A2[0, :40] = a; B2[0, :90] = b
