@@ -65,13 +65,24 @@ template <int UP> __global__ void __launch_bounds__(kThreads) resample_kernel(Re
     double acc[TO];
 #pragma unroll
     for (int a = 0; a < TO; ++a) acc[a] = 0.0;
+    // the taps of the NEXT step are requested before this step's 8 UP multiply-adds: with two CTAs of four warps
+    // per SM (80 KB of staged input each) nothing else hides the L2 round trip of the tap loads
+    double hn[UP];
+#pragma unroll
+    for (int ph = 0; ph < UP; ++ph) hn[ph] = tid < p.qmax ? __ldg(p.hpoly + (size_t)ph * p.qmax + tid) : 0.0;
     for (int q = tid; q < p.qmax; q += kThreads) {
         const double* xq = xs + (p.qmax - 1 - q);
+        double hv[UP];
+#pragma unroll
+        for (int ph = 0; ph < UP; ++ph) hv[ph] = hn[ph];
+        if (q + kThreads < p.qmax) {
+#pragma unroll
+            for (int ph = 0; ph < UP; ++ph) hn[ph] = __ldg(p.hpoly + (size_t)ph * p.qmax + q + kThreads);
+        }
 #pragma unroll
         for (int ph = 0; ph < UP; ++ph) {
-            const double hv = __ldg(p.hpoly + (size_t)ph * p.qmax + q);
 #pragma unroll
-            for (int k = 0; k < kPerPhase; ++k) acc[ph * kPerPhase + k] = fma(hv, xq[p.rel[ph * kPerPhase + k]], acc[ph * kPerPhase + k]);
+            for (int k = 0; k < kPerPhase; ++k) acc[ph * kPerPhase + k] = fma(hv[ph], xq[p.rel[ph * kPerPhase + k]], acc[ph * kPerPhase + k]);
         }
     }
 #pragma unroll
