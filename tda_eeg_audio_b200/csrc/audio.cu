@@ -7,12 +7,13 @@
 //                             tda_filtfilt_f64, form 1)
 //
 // resample: only the KEPT outputs are computed (scipy's upfirdn does the same).  One CTA owns a
-// tile of 8*UP consecutive outputs of one sequence; the input span the tile needs (~10k samples,
-// each used by ~20 (output, tap) pairs) is staged once in shared memory with coalesced loads,
+// tile of 4*UP consecutive outputs of one sequence; the input span the tile needs (~6k samples)
+// is staged once in shared memory with coalesced loads,
 // every thread walks a strided slice of the polyphase taps (coalesced, L2-resident: the filter is
-// 140 KB) and keeps all 8*UP partial sums in registers; warp shuffles + one shared-memory pass
-// finish the dot products.  Shared-memory bound (one LDS.64 per FMA), ~20 ms for the full
-// 1,416-recording data set against 81 ms per recording on the CPU.
+// 140 KB, the taps of the next step requested one step ahead) and keeps all 4*UP partial sums in
+// registers; warp shuffles + one shared-memory pass finish the dot products.  One LDS.64 per FMA;
+// four CTAs of four warps per SM.  ~45 ms for the full 1,416-recording data set against 81 ms per
+// recording on the CPU.
 // hilbert: cuFFT Z2Z (plain library FFT; N = 15,000 = 2^3 3 5^4) between two elementwise kernels.
 #include <cuda_runtime.h>
 #include <cufft.h>
@@ -29,7 +30,7 @@ namespace tda {
 namespace audio {
 
 constexpr int kMaxUp = 8;
-constexpr int kPerPhase = 8;
+constexpr int kPerPhase = 4;   // outputs per phase and tile (measured 8 / 4 / 2: 4.45 / 3.77 / 4.35 ms for 96 recordings: staged span against tap reuse)
 constexpr int kThreads = 128;
 
 struct ResParams {
