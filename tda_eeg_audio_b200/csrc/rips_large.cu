@@ -1768,7 +1768,9 @@ static bool make_plan(int B, int N, size_t ws_bytes, Plan& pl) {
         pl.nanflag = o; o += al((size_t)C * 4);
         pl.list = o; o += al((size_t)C * 4);
         pl.list0 = o; o += al((size_t)C * 4);
-        pl.sortbuf = o; o += al((size_t)C * pl.Emax * 16);
+        // sort ping-pong of the grid-wide sort (16 bytes per edge); up to 256 points the sort lives in shared memory
+        // and the region only holds the list of tie-run members left to the rank-row walk (8 bytes per edge at most)
+        pl.sortbuf = o; o += al((size_t)C * pl.Emax * (N > 256 ? 16 : 8));
         pl.skey = o; o += al((size_t)C * pl.Emax * 4);
         pl.P = o; o += al((size_t)C * pl.Emax * 4);
         pl.defv = o; o += al((size_t)C * pl.Emax * 2);
